@@ -1,0 +1,26 @@
+"""cub_b200 -- B200-native (sm_100a) drop-in for the cub::DeviceRadixSort hot path.
+
+Layout:
+  csrc/                 hand-written CUDA kernels + the C-ABI (include/b2s_radix_sort.h)
+  device_radix_sort.py  host-side mirror of cub::DeviceRadixSort (same entry points / argument meaning)
+  multi_gpu.py          single-box multi-GPU SortPairs (one process per GPU, NCCL all-to-all)
+"""
+from .device_radix_sort import (  # noqa: F401
+    DeviceRadixSort,
+    DoubleBuffer,
+    KEY_TYPES,
+    key_type_of,
+    sort_keys,
+    sort_pairs,
+    sort_pairs_host,
+)
+
+__all__ = [
+    "DeviceRadixSort",
+    "DoubleBuffer",
+    "KEY_TYPES",
+    "key_type_of",
+    "sort_keys",
+    "sort_pairs",
+    "sort_pairs_host",
+]

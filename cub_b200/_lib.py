@@ -1,0 +1,68 @@
+"""ctypes binding of the product C-ABI (include/b2s_radix_sort.h -> cub_b200/libb2s.so).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C cub_b200/csrc``.
+There is NO fallback: if the CUDA library is missing, importing a sort entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2s.so")
+
+_c = ctypes
+_SORT_ARGS = [
+    _c.c_void_p, _c.POINTER(_c.c_size_t),            # d_temp_storage, temp_storage_bytes
+    _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # keys_in, keys_out, values_in, values_out
+    _c.c_uint64, _c.c_int, _c.c_int, _c.c_int,        # num_items, key_type, value_bytes, offset_bytes
+    _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,        # descending, begin_bit, end_bit, stream
+]
+_SORT_DB_ARGS = [
+    _c.c_void_p, _c.POINTER(_c.c_size_t),
+    _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int),    # key_bufs[2], key_selector
+    _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int),    # val_bufs[2], val_selector
+    _c.c_uint64, _c.c_int, _c.c_int, _c.c_int,
+    _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+]
+
+# every symbol include/b2s_radix_sort.h declares: name -> (restype, argtypes)
+EXPORTS = {
+    "b2s_radix_sort": (_c.c_int, _SORT_ARGS),
+    "b2s_radix_sort_db": (_c.c_int, _SORT_DB_ARGS),
+    "b2s_key_bytes": (_c.c_int, [_c.c_int]),
+    "b2s_version": (_c.c_char_p, []),
+    "b2s_last_launch_count": (_c.c_int, []),
+    "b2s_lower_bound": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "b2s_fill_keys": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_void_p]),
+    "b2s_fill_iota": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_void_p]),
+    "b2s_check_sorted": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                    _c.c_int, _c.c_void_p, _c.c_void_p]),
+}
+
+_lib = None
+
+
+def bind(lib: ctypes.CDLL, prefix: str = "b2s") -> ctypes.CDLL:
+    """Attach prototypes. ``prefix`` lets the test-only reference shims (same signatures,
+    ``ref_cub_*`` / ``tk_cub_*`` symbols) reuse the two sort prototypes."""
+    for name, (res, args) in EXPORTS.items():
+        sym = name if prefix == "b2s" else name.replace("b2s", prefix, 1)
+        if prefix != "b2s" and name not in ("b2s_radix_sort", "b2s_radix_sort_db"):
+            continue
+        fn = getattr(lib, sym)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C cub_b200/csrc`. cub_b200 has no CPU or PyTorch fallback."
+            )
+        _lib = bind(ctypes.CDLL(LIB_PATH))
+    return _lib

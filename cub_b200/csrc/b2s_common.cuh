@@ -1,0 +1,198 @@
+// b2s_common.cuh -- shared device helpers of the B200 radix sort (sm_100a only).
+//
+// Key bit-ordering arithmetic mirrors the reference semantics (NOT its code):
+//   cub/util_type.cuh:1031,1078,1179        Traits<T>::TwiddleIn (unsigned / signed / floating)
+//   cub/block/radix_rank_sort_operations.cuh:592-599  descending = complement of the bit-ordered key
+//   cub/block/radix_rank_sort_operations.cuh:79-89    -0.0 collapses onto +0.0 for DIGIT extraction only
+// Here all of that is folded into one per-pass "digit functor" driven by three runtime
+// constants so that one kernel instantiation serves unsigned, signed, ascending and
+// descending keys of a given width (floating keys use a second instantiation).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef __CUDA_ARCH__
+#define B2S_DEVICE_ARCH_OK 1
+#elif __CUDA_ARCH__ >= 1000
+#define B2S_DEVICE_ARCH_OK 1
+#else
+#error "b2s kernels are written for sm_100a only"
+#endif
+
+namespace b2s {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+
+template <int BYTES> struct UIntOf;
+template <> struct UIntOf<1> { using type = uint8_t; };
+template <> struct UIntOf<2> { using type = uint16_t; };
+template <> struct UIntOf<4> { using type = uint32_t; };
+template <> struct UIntOf<8> { using type = unsigned long long; };
+struct alignas(16) U128 { unsigned long long lo, hi; };
+template <> struct UIntOf<16> { using type = U128; };
+
+// Register-width type a key is widened to for arithmetic (8/16-bit keys compute in 32 bits).
+template <int BYTES> struct WideOf { using type = uint32_t; };
+template <> struct WideOf<8> { using type = unsigned long long; };
+
+// ---------------------------------------------------------------------------------------
+// Digit functor.  digit(k) = ((collapse(k) ^ flip(k)) >> bit) & mask
+//   integer keys : flip = xor_mask                       (sign bit for signed, all ones more for descending)
+//   floating keys: flip = xor_mask ^ (k<0 ? ~HIGH : 0)   with xor_mask = HIGH (asc) or ~HIGH... folded below
+//   collapse     : k == zero_from ? zero_to : k          (floating only; raw -0.0 -> +0.0 ascending,
+//                                                          raw +0.0 -> -0.0 descending == the reference's
+//                                                          post-twiddle rule expressed on raw bits)
+// ---------------------------------------------------------------------------------------
+template <int KBYTES, bool IS_FLOAT>
+struct DigitOp {
+  using W = typename WideOf<KBYTES>::type;
+  W xor_mask;    // integer: HIGH (signed) ^ ONES (descending); float: ONES if descending else 0
+  W zero_from;   // float only
+  W zero_to;     // float only
+  uint32_t bit;  // first bit of this pass' digit
+  uint32_t mask; // (1 << digit_bits) - 1
+
+  static constexpr int KBITS = KBYTES * 8;
+  static constexpr W ONES = KBYTES == 8 ? ~W(0) : (W)((1ull << (KBITS % 64)) - 1);
+  static constexpr W HIGH = W(1) << (KBITS - 1);
+
+  __device__ __forceinline__ W ordered(W k) const {
+    if (IS_FLOAT) {
+      k = (k == zero_from) ? zero_to : k;
+      // Traits<fp>::TwiddleIn: negative -> flip all bits, non-negative -> flip the sign bit.
+      W neg = (k & HIGH) ? ONES : HIGH;
+      return k ^ neg ^ xor_mask;
+    } else {
+      return k ^ xor_mask;
+    }
+  }
+  __device__ __forceinline__ uint32_t operator()(W k) const { return (uint32_t)(ordered(k) >> bit) & mask; }
+};
+
+// Host-side description of a key type, resolved once per call.
+struct KeyDesc {
+  int bytes;       // 1,2,4,8
+  int category;    // 0 unsigned, 1 signed, 2 floating
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B2S_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B2S_DONE_%=;\n"
+      "bra B2S_WAIT_%=;\n"
+      "B2S_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); 16-byte aligned src/dst/size.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// gpu-scope relaxed loads / stores for the look-back status words (the word carries flag AND
+// value, so no acquire/release pairing is needed; L1 is bypassed by the scope).
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t lanemask_le() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+  return m;
+}
+
+// Peer mask of lanes holding the same BITS-bit digit: one ballot per digit bit, 4 SASS
+// instructions per bit (LOP3->P, VOTE, @!P LOP3, LOP3).
+template <int I>
+__device__ __forceinline__ void match_bit(uint32_t& m, uint32_t d) {
+  asm volatile("{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t, b;\n"
+      "and.b32 t, %1, %2;\n"
+      "setp.ne.u32 p, t, 0;\n"
+      "vote.sync.ballot.b32 b, p, 0xffffffff;\n"
+      "@!p not.b32 b, b;\n"
+      "and.b32 %0, %0, b;\n"
+      "}\n"
+      : "+r"(m)
+      : "r"(d), "n"(1u << I));
+}
+template <int BITS>
+__device__ __forceinline__ uint32_t match_ballot(uint32_t d) {
+  uint32_t m = 0xffffffffu;
+  match_bit<0>(m, d);
+  if (BITS > 1) match_bit<1>(m, d);
+  if (BITS > 2) match_bit<2>(m, d);
+  if (BITS > 3) match_bit<3>(m, d);
+  if (BITS > 4) match_bit<4>(m, d);
+  if (BITS > 5) match_bit<5>(m, d);
+  if (BITS > 6) match_bit<6>(m, d);
+  if (BITS > 7) match_bit<7>(m, d);
+  return m;
+}
+// Hardware MATCH.ANY variant.
+__device__ __forceinline__ uint32_t match_hw(uint32_t d) { return __match_any_sync(0xffffffffu, d); }
+
+// index of the most significant set bit (SASS FLO)
+__device__ __forceinline__ uint32_t bfind(uint32_t x) {
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+// Leader-only shared-memory fetch-add, predicated (no branch): returns the old value on the
+// leader lane, 0 elsewhere.
+__device__ __forceinline__ uint32_t atoms_add_if(bool pred, uint32_t smem_addr, uint32_t v) {
+  uint32_t old = 0;
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "setp.ne.u32 p, %3, 0;\n"
+               "@p atom.shared.add.u32 %0, [%1], %2;\n"
+               "}\n"
+               : "+r"(old)
+               : "r"(smem_addr), "r"(v), "r"((uint32_t)pred)
+               : "memory");
+  return old;
+}
+
+}  // namespace b2s

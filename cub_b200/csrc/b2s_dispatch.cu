@@ -1,0 +1,284 @@
+// b2s_dispatch.cu -- host side of the B200 radix sort + the C-ABI of include/b2s_radix_sort.h.
+//
+// Mirrors the BEHAVIOUR of the reference host path (not its code):
+//   cub::DeviceRadixSort entry points                 cub/device/device_radix_sort.cuh:312,781,1214,1675,2106,2525,2921,3330
+//   DispatchRadixSort::Invoke / InvokeCopy            cub/device/dispatch/dispatch_radix_sort.cuh:1939-1978, 1885-1934
+//   DispatchRadixSort::InvokeOnesweep                 cub/device/dispatch/dispatch_radix_sort.cuh:1521-1727
+//   AliasTemporaries (256-byte carving, size query)   cub/util_device.cuh:68-109
+//
+// What is different by design: no <=2^28-item "portions" (64-bit look-back words for
+// n >= 2^30 instead), ONE memset per sort (counters + histogram + first status array; each
+// pass clears the status array of the next one), histogram + exclusive scan in one launch:
+// a sort of P digit passes is 1 memset + 1 + P kernel launches.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/b2s_radix_sort.h"
+#include "b2s_internal.h"
+
+namespace b2s {
+namespace {
+
+struct KeyInfo {
+  int bytes;
+  int category;  // 0 unsigned, 1 signed, 2 floating
+};
+const KeyInfo kKeyInfo[B2S_KEY_TYPE_COUNT] = {
+    {1, 0}, {1, 1}, {2, 0}, {2, 1}, {2, 2}, {2, 2}, {4, 0}, {4, 1}, {4, 2}, {8, 0}, {8, 1}, {8, 2},
+};
+
+thread_local int g_last_launches = 0;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+DigitConsts make_consts(const KeyInfo& ki, bool descending) {
+  const int bits = ki.bytes * 8;
+  const uint64_t ones = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+  const uint64_t high = 1ull << (bits - 1);
+  DigitConsts dc{};
+  dc.is_float = ki.category == 2;
+  if (dc.is_float) {
+    dc.xor_mask = descending ? ones : 0;
+    dc.zero_from = descending ? 0 : high;
+    dc.zero_to = descending ? high : 0;
+    dc.pad_key = descending ? ones : (ones ^ high);  // -NaN(all ones) / +NaN(0x7f..f) order last
+  } else {
+    dc.xor_mask = (ki.category == 1 ? high : 0) ^ (descending ? ones : 0);
+    dc.pad_key = ones ^ dc.xor_mask;
+  }
+  return dc;
+}
+
+int tuning_variant() {
+  static int v = [] {
+    const char* e = std::getenv("B2S_VARIANT");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
+}
+
+struct KernelSet {
+  cudaError_t (*hist)(const HistArgs&, cudaStream_t);
+  cudaError_t (*onesweep)(int, const PassArgs&, cudaStream_t);
+  int (*tile)(int, int);
+  int (*num_variants)();
+};
+const KernelSet* kernels_for(int kbytes) {
+  static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1};
+  static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2};
+  static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4};
+  static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8};
+  switch (kbytes) {
+    case 1: return &k1;
+    case 2: return &k2;
+    case 4: return &k4;
+    case 8: return &k8;
+    default: return nullptr;
+  }
+}
+
+int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
+
+// Temp-storage carving.
+struct Layout {
+  size_t off_ctrs, off_hist, off_status0, off_status1, off_keys, off_vals, total;
+  size_t zero_bytes;  // [off_ctrs, off_ctrs + zero_bytes) is cleared once per sort
+};
+
+Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off64, bool need_alt) {
+  Layout L{};
+  const size_t osz = off64 ? 8 : 4;
+  const uint64_t tiles = (n + tile - 1) / tile;
+  size_t o = 0;
+  L.off_ctrs = o;      o += align_up(sizeof(unsigned int) * (size_t)(1 + passes), 256);
+  L.off_hist = o;      o += align_up(osz * 256 * (size_t)passes, 256);
+  L.off_status0 = o;   o += align_up(osz * 256 * tiles, 256);
+  L.zero_bytes = o;
+  L.off_status1 = o;   o += passes > 1 ? align_up(osz * 256 * tiles, 256) : 0;
+  L.off_keys = o;      o += need_alt ? align_up((size_t)n * kbytes, 256) : 0;
+  L.off_vals = o;      o += (need_alt && vbytes) ? align_up((size_t)n * vbytes, 256) : 0;
+  L.total = o + 255;   // slack so any d_temp_storage alignment works
+  return L;
+}
+
+// The shared implementation of both API forms.
+//   overwrite == false: pointer form  (kin -> kout, kin never written)
+//   overwrite == true : DoubleBuffer form (k[0]/k[1] ping-pong, selector returned)
+int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], int* selector_out, bool overwrite,
+              uint64_t n, int key_type, int vbytes, bool descending, int begin_bit, int end_bit,
+              cudaStream_t stream) {
+  g_last_launches = 0;
+  if (!temp_bytes) return (int)cudaErrorInvalidValue;
+  if (key_type < 0 || key_type >= B2S_KEY_TYPE_COUNT) return (int)cudaErrorInvalidValue;
+  if (!(vbytes == 0 || vbytes == 1 || vbytes == 2 || vbytes == 4 || vbytes == 8 || vbytes == 16))
+    return (int)cudaErrorInvalidValue;
+  const KeyInfo ki = kKeyInfo[key_type];
+  const int kbytes = ki.bytes;
+  const int num_bits = end_bit - begin_bit;
+  if (selector_out) *selector_out = 0;
+
+  // Trivial cases (dispatch_radix_sort.cuh:1945-1963)
+  if (n == 0 || (num_bits <= 0 && overwrite)) {
+    if (!d_temp) *temp_bytes = 1;
+    return (int)cudaSuccess;
+  }
+  if (num_bits <= 0) {
+    if (!d_temp) { *temp_bytes = 1; return (int)cudaSuccess; }
+    cudaError_t e = cudaMemcpyAsync(kbuf[1], kbuf[0], (size_t)n * kbytes, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return (int)e;
+    g_last_launches++;
+    if (vbytes) {
+      e = cudaMemcpyAsync(vbuf[1], vbuf[0], (size_t)n * vbytes, cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) return (int)e;
+      g_last_launches++;
+    }
+    return (int)cudaSuccess;
+  }
+
+  const KernelSet* ks = kernels_for(kbytes);
+  int variant = tuning_variant();
+  if (variant < 0 || variant >= ks->num_variants()) variant = 0;
+  const int tile = ks->tile(variant, vbytes);
+  const int passes = (num_bits + 7) / 8;
+  const bool off64 = n >= (1ull << 30);
+  const bool need_alt = !overwrite && passes > 1;
+  const Layout L = carve(n, kbytes, vbytes, passes, tile, off64, need_alt);
+
+  if (!d_temp) {
+    *temp_bytes = L.total;
+    return (int)cudaSuccess;
+  }
+  if (*temp_bytes < L.total) return (int)cudaErrorInvalidValue;
+
+  unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(d_temp), 256));
+  unsigned int* ctrs = reinterpret_cast<unsigned int*>(base + L.off_ctrs);
+  unsigned char* hist = base + L.off_hist;
+  unsigned char* status[2] = {base + L.off_status0, base + L.off_status1};
+  const size_t osz = off64 ? 8 : 4;
+
+  cudaError_t e = cudaMemsetAsync(base + L.off_ctrs, 0, L.zero_bytes, stream);
+  if (e != cudaSuccess) return (int)e;
+  g_last_launches++;
+
+  const DigitConsts dc = make_consts(ki, descending);
+
+  HistArgs h{};
+  h.keys = kbuf[0];
+  h.n = n;
+  h.dc = dc;
+  h.begin_bit = begin_bit;
+  h.end_bit = end_bit;
+  h.num_passes = passes;
+  h.ghist = hist;
+  h.done = ctrs;
+  h.off64 = off64;
+  {
+    const uint64_t vecs = (n * kbytes + 16 * 512 - 1) / (16 * 512);  // CTAs worth of 128-bit loads
+    uint64_t g = (uint64_t)sm_count() * 4;
+    if (g > vecs) g = vecs ? vecs : 1;
+    h.grid = (int)g;
+  }
+  e = ks->hist(h, stream);
+  if (e != cudaSuccess) return (int)e;
+  g_last_launches++;
+
+  // Ping-pong plan.  Pointer form: in -> {tmp,out} alternating so that the last pass lands in
+  // `out` and `in` is only ever read.  DoubleBuffer form: the two user buffers alternate.
+  void* ktmp = need_alt ? base + L.off_keys : nullptr;
+  void* vtmp = (need_alt && vbytes) ? base + L.off_vals : nullptr;
+  const void* ksrc = kbuf[0];
+  const void* vsrc = vbytes ? vbuf[0] : nullptr;
+  int cur = 0;  // DoubleBuffer: index of the buffer holding the current data
+  for (int p = 0; p < passes; ++p) {
+    void* kdst;
+    void* vdst;
+    if (overwrite) {
+      kdst = kbuf[cur ^ 1];
+      vdst = vbytes ? vbuf[cur ^ 1] : nullptr;
+    } else {
+      const bool to_out = ((passes - 1 - p) & 1) == 0;
+      kdst = to_out ? kbuf[1] : ktmp;
+      vdst = vbytes ? (to_out ? vbuf[1] : vtmp) : nullptr;
+    }
+    PassArgs a{};
+    a.keys_in = ksrc;
+    a.keys_out = kdst;
+    a.vals_in = vsrc;
+    a.vals_out = vdst;
+    a.status = status[p & 1];
+    a.status_next = (p + 1 < passes) ? status[(p + 1) & 1] : nullptr;
+    a.bins = hist + osz * 256 * (size_t)p;
+    a.tile_counter = ctrs + 1 + p;
+    a.n = n;
+    a.dc = dc;
+    a.bit = begin_bit + 8 * p;
+    a.nbits = (end_bit - a.bit) < 8 ? (end_bit - a.bit) : 8;
+    a.off64 = off64;
+    a.vbytes = vbytes;
+    e = ks->onesweep(variant, a, stream);
+    if (e != cudaSuccess) return (int)e;
+    g_last_launches++;
+    ksrc = kdst;
+    vsrc = vdst;
+    cur ^= 1;
+  }
+  if (selector_out) *selector_out = overwrite ? cur : 0;
+  return (int)cudaSuccess;
+}
+
+}  // namespace
+}  // namespace b2s
+
+extern "C" {
+
+int b2s_radix_sort(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, void* d_keys_out,
+                   const void* d_values_in, void* d_values_out, uint64_t num_items, int key_type, int value_bytes,
+                   int offset_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream) {
+  (void)offset_bytes;
+  void* k[2] = {const_cast<void*>(d_keys_in), d_keys_out};
+  void* v[2] = {const_cast<void*>(d_values_in), d_values_out};
+  return b2s::sort_impl(d_temp_storage, temp_storage_bytes, k, v, nullptr, false, num_items, key_type, value_bytes,
+                        descending != 0, begin_bit, end_bit, (cudaStream_t)stream);
+}
+
+int b2s_radix_sort_db(void* d_temp_storage, size_t* temp_storage_bytes, void* key_bufs[2], int* key_selector,
+                      void* val_bufs[2], int* val_selector, uint64_t num_items, int key_type, int value_bytes,
+                      int offset_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream) {
+  (void)offset_bytes;
+  if (!key_bufs || !key_selector) return (int)cudaErrorInvalidValue;
+  if (value_bytes && (!val_bufs || !val_selector)) return (int)cudaErrorInvalidValue;
+  const int ks = *key_selector & 1;
+  const int vs = value_bytes ? (*val_selector & 1) : 0;
+  void* k[2] = {key_bufs[ks], key_bufs[ks ^ 1]};
+  void* v[2] = {value_bytes ? val_bufs[vs] : nullptr, value_bytes ? val_bufs[vs ^ 1] : nullptr};
+  int flipped = 0;
+  const int r = b2s::sort_impl(d_temp_storage, temp_storage_bytes, k, v, &flipped, true, num_items, key_type,
+                               value_bytes, descending != 0, begin_bit, end_bit, (cudaStream_t)stream);
+  if (r == 0 && d_temp_storage) {
+    *key_selector = ks ^ flipped;
+    if (value_bytes) *val_selector = vs ^ flipped;
+  }
+  return r;
+}
+
+int b2s_key_bytes(int key_type) {
+  return (key_type >= 0 && key_type < B2S_KEY_TYPE_COUNT) ? b2s::kKeyInfo[key_type].bytes : 0;
+}
+
+const char* b2s_version(void) { return "b2s 0.1 sm_100a"; }
+
+int b2s_last_launch_count(void) { return b2s::g_last_launches; }
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// b2s_internal.h -- host-side interfaces between the dispatch layer and the per-key-width
+// kernel translation units (split so the instantiations compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b2s {
+
+// Runtime constants of one sort call that parameterise the digit functor (see b2s_common.cuh).
+struct DigitConsts {
+  uint64_t xor_mask;
+  uint64_t zero_from;
+  uint64_t zero_to;
+  uint64_t pad_key;  // raw key that orders last (bit-ordered form all ones)
+  bool is_float;
+};
+
+struct HistArgs {
+  const void* keys;
+  uint64_t n;
+  DigitConsts dc;
+  int begin_bit, end_bit, num_passes;
+  void* ghist;
+  unsigned int* done;
+  bool off64;
+  int grid;
+};
+
+struct PassArgs {
+  const void* keys_in;
+  void* keys_out;
+  const void* vals_in;
+  void* vals_out;
+  void* status;
+  void* status_next;
+  const void* bins;
+  unsigned int* tile_counter;
+  uint64_t n;
+  DigitConsts dc;
+  int bit;       // first bit of the digit
+  int nbits;     // digit width of this pass (<= 8)
+  bool off64;
+  int vbytes;
+};
+
+// One tuning point of the onesweep kernel.
+struct Variant {
+  int nt, ipt, minb, match;
+};
+
+// Implemented once per key width in b2s_kernels_k{1,2,4,8}.cu
+#define B2S_DECL_K(K)                                                                         \
+  cudaError_t hist_launch_k##K(const HistArgs& a, cudaStream_t s);                            \
+  cudaError_t onesweep_launch_k##K(int variant, const PassArgs& a, cudaStream_t s);           \
+  int onesweep_tile_k##K(int variant, int vbytes);                                            \
+  int onesweep_num_variants_k##K();                                                           \
+  Variant onesweep_variant_k##K(int variant, int vbytes);
+B2S_DECL_K(1)
+B2S_DECL_K(2)
+B2S_DECL_K(4)
+B2S_DECL_K(8)
+#undef B2S_DECL_K
+
+}  // namespace b2s

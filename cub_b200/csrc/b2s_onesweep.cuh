@@ -1,0 +1,269 @@
+// b2s_onesweep.cuh -- one digit pass of the LSD sort: stable partition of all n items by one
+// 8-bit digit into their global positions, chained-scan ("onesweep") style.
+//
+// Replaces (reference, for parity of RESULT only):
+//   DeviceRadixSortOnesweepKernel  cub/device/dispatch/dispatch_radix_sort.cuh:580
+//   AgentRadixSortOnesweep         cub/agent/agent_radix_sort_onesweep.cuh:98-688
+//   BlockRadixRankMatchEarlyCounts cub/block/block_radix_rank.cuh:898-1192
+//
+// B200-first structure (what differs from the reference kernel):
+//   * the tile's keys AND values are staged global->shared by the TMA engine
+//     (cp.async.bulk + mbarrier; SASS UBLKCP) issued by one thread at CTA start: no per-item
+//     LDG instructions, no registers held by loads in flight, values prefetched for free while
+//     the keys are being ranked;  unaligned / partial tiles fall back to element loads;
+//   * several small CTAs per SM (tile 3-6 K items) so that load / rank / scatter phases of
+//     different tiles overlap on one SM instead of one 12-warp CTA serialising them;
+//   * single ranking sweep: warp-private digit counters are produced BY the match ranking
+//     (one leader atomic per (row, digit)), no separate counting sweep;
+//   * keys and values are reordered in shared memory in ONE sweep and written out in ONE
+//     sweep (4 block barriers per tile), so digits / offsets are never cached across phases;
+//   * look-back status words are gpu-scope relaxed (not system-scope volatile), one status
+//     array per pass parity: a pass clears the NEXT pass' array, so the whole sort needs a
+//     single memset; 64-bit status words when n >= 2^30 instead of <=2^28-item portions;
+//   * the first look-back load is issued before the shared-memory scatter to hide its latency.
+//
+// Stability: items are ranked in tile order (warp-striped rows, lane order inside a row,
+// rows in program order); tiles are ordered by the dynamic tile id == position in the input.
+#pragma once
+#include "b2s_common.cuh"
+
+namespace b2s {
+
+enum MatchMode { MATCH_BALLOT = 0, MATCH_HW = 1 };
+
+template <int KBYTES, bool IS_FLOAT>
+struct OnesweepParams {
+  const void* keys_in;
+  void* keys_out;
+  const void* vals_in;
+  void* vals_out;
+  void* status;        // OffT[num_tiles][256], zero on entry
+  void* status_next;   // OffT[num_tiles][256] cleared here for the next pass (may be null)
+  const void* bins;    // OffT[256] exclusive digit offsets of this pass
+  unsigned int* tile_counter;
+  unsigned long long n;
+  unsigned long long pad_key;  // raw key whose bit-ordered form is all ones
+  DigitOp<KBYTES, IS_FLOAT> op;
+};
+
+template <int KBYTES, int VBYTES, int NT, int IPT>
+struct OnesweepSmem {
+  static constexpr int TILE = NT * IPT;
+  static constexpr int NW = NT / 32;
+  static constexpr int KEY_BYTES = TILE * KBYTES + 16;
+  static constexpr int VAL_BYTES = VBYTES ? TILE * VBYTES + 16 : 0;
+  static constexpr int OFF_KEYS = 0;
+  static constexpr int OFF_VALS = (KEY_BYTES + 127) / 128 * 128;
+  static constexpr int OFF_WHIST = OFF_VALS + (VAL_BYTES + 127) / 128 * 128;
+  static constexpr int OFF_GOFF = OFF_WHIST + NW * RADIX * 4;
+  static constexpr int OFF_MISC = OFF_GOFF + RADIX * 8;
+  static constexpr int TOTAL = OFF_MISC + 128;
+};
+
+template <int KBYTES, int VBYTES, bool IS_FLOAT, typename OffT, int NT, int IPT, int MINB, int MATCH>
+__global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, IS_FLOAT> P) {
+  using KeyU = typename UIntOf<KBYTES>::type;
+  using W = typename WideOf<KBYTES>::type;
+  using ValU = typename UIntOf<VBYTES ? VBYTES : 1>::type;
+  using L = OnesweepSmem<KBYTES, VBYTES, NT, IPT>;
+  constexpr int TILE = L::TILE;
+  constexpr int NW = L::NW;
+  constexpr bool HAS_VALUES = VBYTES != 0;
+  constexpr int OBITS = sizeof(OffT) * 8;
+  constexpr OffT FLAG_INCLUSIVE = OffT(1) << (OBITS - 1);
+  constexpr OffT FLAG_PARTIAL = OffT(1) << (OBITS - 2);
+  constexpr OffT VALUE_MASK = FLAG_PARTIAL - 1;
+  static_assert(NT >= RADIX && NT % 32 == 0, "one thread per digit needed");
+  static_assert(32 * IPT < 65536, "warp-bucket rank is packed into 16 bits");
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* stage_k = smem + L::OFF_KEYS;
+  unsigned char* stage_v = smem + L::OFF_VALS;
+  unsigned int* whist = reinterpret_cast<unsigned int*>(smem + L::OFF_WHIST);
+  OffT* s_goff = reinterpret_cast<OffT*>(smem + L::OFF_GOFF);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_MISC);            // [2]
+  unsigned int* s_wtot = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 16);  // [8]
+  unsigned int* s_tile = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 64);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  // ---- P0: claim a tile (launch order == input order), arm the barriers, clear counters
+  if (tid == 0) {
+    *s_tile = atomicAdd(P.tile_counter, 1u);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+#pragma unroll
+  for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
+  __syncthreads();
+
+  const unsigned long long tile = *s_tile;
+  const unsigned long long tile_base = tile * TILE;
+  const unsigned long long remain = P.n - tile_base;
+  const bool full = remain >= (unsigned long long)TILE;
+  const int valid = full ? TILE : (int)remain;
+
+  const KeyU* gkeys = reinterpret_cast<const KeyU*>(P.keys_in) + tile_base;
+  const ValU* gvals = reinterpret_cast<const ValU*>(P.vals_in) + tile_base;
+
+  // TMA path needs 16-byte aligned source windows that stay inside the arrays.
+  const uintptr_t kaddr = reinterpret_cast<uintptr_t>(gkeys);
+  const uintptr_t vaddr = reinterpret_cast<uintptr_t>(gvals);
+  unsigned int kshift = (unsigned int)(kaddr & 15);
+  unsigned int vshift = HAS_VALUES ? (unsigned int)(vaddr & 15) : 0;
+  const unsigned int kbytes = (kshift + TILE * KBYTES + 15u) & ~15u;
+  const unsigned int vbytes = (vshift + TILE * VBYTES + 15u) & ~15u;
+  bool bulk = full && (tile > 0 || (kshift == 0 && vshift == 0));
+  bulk = bulk && (kshift == 0 || remain * KBYTES >= (unsigned long long)kbytes - kshift) &&
+         (vshift == 0 || remain * VBYTES >= (unsigned long long)vbytes - vshift);
+
+  if (bulk) {
+    if (tid == 0) {
+      mbar_expect_tx(&bar[0], kbytes);
+      bulk_g2s(stage_k, reinterpret_cast<const void*>(kaddr - kshift), kbytes, &bar[0]);
+      if (HAS_VALUES) {
+        mbar_expect_tx(&bar[1], vbytes);
+        bulk_g2s(stage_v, reinterpret_cast<const void*>(vaddr - vshift), vbytes, &bar[1]);
+      }
+    }
+  } else {
+    kshift = 0;
+    vshift = 0;
+    KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
+    // a partial tile is padded with a key whose digit is the largest one in every pass, so
+    // the padding ranks after all real items and is never written out
+    for (int i = tid; i < TILE; i += NT) sk[i] = i < valid ? gkeys[i] : (KeyU)P.pad_key;
+    if (HAS_VALUES) {
+      ValU* sv = reinterpret_cast<ValU*>(stage_v);
+      for (int i = tid; i < valid; i += NT) sv[i] = gvals[i];
+    }
+    __syncthreads();
+  }
+
+  // ---- P1: keys -> registers (warp-striped rows), match-rank inside the warp
+  const int warp_base = warp * 32 * IPT;
+  W key[IPT];
+  unsigned int rk[IPT];  // (digit << 16) | rank inside this warp's digit bucket
+  {
+    if (bulk) mbar_wait(&bar[0], 0);
+    const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + kshift);
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) key[u] = (W)sk[warp_base + u * 32 + lane];
+  }
+  const auto op = P.op;
+  unsigned int* myhist = whist + warp * RADIX;
+  const unsigned int myhist_s = smem_u32(myhist);
+  const unsigned int lt = lanemask_lt();
+#pragma unroll
+  for (int u = 0; u < IPT; ++u) {
+    const unsigned int d = op(key[u]);
+    const unsigned int m = MATCH == MATCH_HW ? match_hw(d) : match_ballot<RADIX_BITS>(d);
+    const unsigned int leader = bfind(m);  // highest peer lane adds the whole group
+    unsigned int prev = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
+    prev = __shfl_sync(0xffffffffu, prev, leader);
+    rk[u] = (prev + __popc(m & lt)) | (d << 16);
+  }
+  __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
+
+  // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases
+  ValU val[HAS_VALUES ? IPT : 1];
+  if (HAS_VALUES) {
+    if (bulk) mbar_wait(&bar[1], 0);
+    const ValU* sv = reinterpret_cast<const ValU*>(stage_v + vshift);
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
+  }
+  OffT* status = reinterpret_cast<OffT*>(P.status) + tile * RADIX;
+  unsigned int total = 0;
+  unsigned int wcnt[NW];
+  if (tid < RADIX) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      wcnt[w] = whist[w * RADIX + tid];
+      total += wcnt[w];
+    }
+    st_status(status + tid, (tile == 0 ? FLAG_INCLUSIVE : FLAG_PARTIAL) | (OffT)total);
+    if (P.status_next) reinterpret_cast<OffT*>(P.status_next)[tile * RADIX + tid] = 0;
+  }
+  unsigned int incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (tid < RADIX && lane == 31) s_wtot[warp] = incl;
+  __syncthreads();  // S2b
+  unsigned int tile_excl = 0;
+  OffT first = 0;
+  if (tid < RADIX) {
+    unsigned int base = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w)
+      if (w < warp) base += s_wtot[w];
+    tile_excl = base + incl - total;
+    unsigned int run = tile_excl;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      whist[w * RADIX + tid] = run;
+      run += wcnt[w];
+    }
+    // issue the first look-back load early; it is consumed after the shared-memory scatter
+    if (tile > 0) first = ld_status(status - RADIX + tid);
+  }
+  __syncthreads();  // S3: bases ready, staged values consumed
+
+  // ---- P3: reorder keys and values in shared memory
+  {
+    KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
+    ValU* sv = reinterpret_cast<ValU*>(stage_v);
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) {
+      const unsigned int d = rk[u] >> 16;
+      const unsigned int r = (rk[u] & 0xffffu) + myhist[d];
+      sk[r] = (KeyU)key[u];
+      if (HAS_VALUES) sv[r] = val[u];
+    }
+  }
+
+  // ---- look-back: exclusive prefix of this tile for digit `tid`
+  if (tid < RADIX) {
+    OffT excl = 0;
+    if (tile > 0) {
+      const OffT* p = status - RADIX + tid;
+      OffT v = first;
+      while (true) {
+        while ((v & (FLAG_INCLUSIVE | FLAG_PARTIAL)) == 0) v = ld_status(p);
+        excl += v & VALUE_MASK;
+        if (v & FLAG_INCLUSIVE) break;
+        p -= RADIX;
+        v = ld_status(p);
+      }
+      st_status(status + tid, FLAG_INCLUSIVE | (excl + (OffT)total));
+    }
+    s_goff[tid] = reinterpret_cast<const OffT*>(P.bins)[tid] + excl - (OffT)tile_excl;
+  }
+  __syncthreads();  // S4
+
+  // ---- P4: coalesced write-out of digit runs
+  {
+    const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k);
+    const ValU* sv = reinterpret_cast<const ValU*>(stage_v);
+    KeyU* okeys = reinterpret_cast<KeyU*>(P.keys_out);
+    ValU* ovals = reinterpret_cast<ValU*>(P.vals_out);
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) {
+      const int pos = u * NT + tid;
+      if (full || pos < valid) {
+        const KeyU k = sk[pos];
+        const OffT dst = s_goff[op((W)k)] + (OffT)pos;
+        okeys[dst] = k;
+        if (HAS_VALUES) ovals[dst] = sv[pos];
+      }
+    }
+  }
+}
+
+}  // namespace b2s
