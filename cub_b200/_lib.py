@@ -33,6 +33,8 @@ EXPORTS = {
     "b2s_key_bytes": (_c.c_int, [_c.c_int]),
     "b2s_version": (_c.c_char_p, []),
     "b2s_last_launch_count": (_c.c_int, []),
+    "b2s_set_variant": (_c.c_int, [_c.c_int]),
+    "b2s_describe_variant": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int] + [_c.POINTER(_c.c_int)] * 4),
     "b2s_lower_bound": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "b2s_fill_keys": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_void_p]),
     "b2s_fill_iota": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_void_p]),
@@ -59,10 +61,11 @@ def bind(lib: ctypes.CDLL, prefix: str = "b2s") -> ctypes.CDLL:
 def load() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("B2S_LIB", LIB_PATH)  # tuning builds (libb2s_tune.so) are selected explicitly
+        if not os.path.exists(path):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C cub_b200/csrc`. cub_b200 has no CPU or PyTorch fallback."
             )
-        _lib = bind(ctypes.CDLL(LIB_PATH))
+        _lib = bind(ctypes.CDLL(path))
     return _lib

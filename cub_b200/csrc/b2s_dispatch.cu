@@ -51,25 +51,25 @@ DigitConsts make_consts(const KeyInfo& ki, bool descending) {
   return dc;
 }
 
-int tuning_variant() {
-  static int v = [] {
-    const char* e = std::getenv("B2S_VARIANT");
-    return e ? std::atoi(e) : 0;
-  }();
-  return v;
-}
+// Tuning hook: variant 0 is the production tuning; a -DB2S_TUNING build carries more points.
+int g_variant = [] {
+  const char* e = std::getenv("B2S_VARIANT");
+  return e ? std::atoi(e) : 0;
+}();
+int tuning_variant() { return g_variant; }
 
 struct KernelSet {
   cudaError_t (*hist)(const HistArgs&, cudaStream_t);
   cudaError_t (*onesweep)(int, const PassArgs&, cudaStream_t);
   int (*tile)(int, int);
   int (*num_variants)();
+  Variant (*variant)(int, int);
 };
 const KernelSet* kernels_for(int kbytes) {
-  static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1};
-  static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2};
-  static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4};
-  static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8};
+  static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1, onesweep_variant_k1};
+  static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2, onesweep_variant_k2};
+  static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4, onesweep_variant_k4};
+  static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8, onesweep_variant_k8};
   switch (kbytes) {
     case 1: return &k1;
     case 2: return &k2;
@@ -280,5 +280,22 @@ int b2s_key_bytes(int key_type) {
 const char* b2s_version(void) { return "b2s 0.1 sm_100a"; }
 
 int b2s_last_launch_count(void) { return b2s::g_last_launches; }
+
+int b2s_set_variant(int variant) {
+  const int old = b2s::g_variant;
+  b2s::g_variant = variant;
+  return old;
+}
+
+int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, int* ipt, int* minb, int* match) {
+  const b2s::KernelSet* ks = b2s::kernels_for(key_bytes);
+  if (!ks || variant < 0 || variant >= ks->num_variants()) return -1;
+  const b2s::Variant v = ks->variant(variant, value_bytes);
+  if (nt) *nt = v.nt;
+  if (ipt) *ipt = v.ipt;
+  if (minb) *minb = v.minb;
+  if (match) *match = v.match;
+  return ks->num_variants();
+}
 
 }  // extern "C"

@@ -107,15 +107,22 @@ cudaError_t launch_vi(int variant, const PassArgs& a, cudaStream_t s, std::integ
 template <int V, bool F>
 cudaError_t launch_off(int variant, const PassArgs& a, cudaStream_t s) {
   using Seq = std::make_integer_sequence<int, NUM_VARIANTS>;
+#ifdef B2S_TUNING
+  if (a.off64) return cudaErrorInvalidValue;  // tuning builds carry 32-bit offsets only
+  return launch_vi<V, F, uint32_t>(variant, a, s, Seq{});
+#else
   return a.off64 ? launch_vi<V, F, unsigned long long>(variant, a, s, Seq{})
                  : launch_vi<V, F, uint32_t>(variant, a, s, Seq{});
+#endif
 }
 
 template <int V>
 cudaError_t launch_f(int variant, const PassArgs& a, cudaStream_t s) {
+#ifndef B2S_TUNING
   if constexpr (K >= 2) {
     if (a.dc.is_float) return launch_off<V, true>(variant, a, s);
   }
+#endif
   return launch_off<V, false>(variant, a, s);
 }
 

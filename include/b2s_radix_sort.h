@@ -101,6 +101,14 @@ const char *b2s_version(void);
  */
 int b2s_last_launch_count(void);
 
+/* Tuning hooks (not part of the reference API).  Variant 0 is the production tuning of the
+ * digit-pass kernel; a tuning build (-DB2S_TUNING) carries more points.  b2s_set_variant returns
+ * the previous variant; b2s_describe_variant returns the number of variants (or -1) and the
+ * {threads, items/thread, min CTAs/SM, match mode} of one of them. */
+int b2s_set_variant(int variant);
+int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int *threads, int *items_per_thread,
+                         int *min_ctas_per_sm, int *match_mode);
+
 /*
  * Device helpers for the multi-GPU sort (new functionality) and
  * for the test/bench harness.  All enqueue on `stream`, no sync.

@@ -1,0 +1,291 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI, against
+ (1) the golden fixtures made from the reference's own generators/harness,
+ (2) the CPU oracle on seeded inputs for every key type / value width / direction / bit range / edge size,
+ (3) the unmodified reference cub::DeviceRadixSort (oracle/_ref/libref_cub.so) on the same device buffers,
+ (4) size-independent properties (sortedness, multiset checksum, permutation) at BASELINE.json's full sizes.
+Bar: bit-exact keys AND values (integer/byte work).  Test structure follows test/test_device_radix_sort.cu:
+sizes incl. 0/1 (:1649-1670), both back-ends (:1259-1376), mis-aligned temp storage (:1109-1110), pointer form
+leaves the input untouched (:1141-1158), bit sub-ranges for unsigned keys (:1461-1494)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests import harness as H
+
+pytestmark = pytest.mark.gpu
+
+NAME_TO_TYPE = {n: i for i, n in enumerate(H.KEY_NAMES)}
+
+
+def _expect(oracle, raw, vals_np, kt, desc, bb, eb):
+    return oracle.radix_sort(raw, vals_np, kt, desc, bb, eb)
+
+
+def _run_and_compare(b2s, oracle, raw, vals_np, kt, desc=False, bb=0, eb=None, label=""):
+    dk = H.to_dev(raw)
+    dv = H.to_dev(vals_np) if vals_np is not None else None
+    before = dk.clone()
+    ko, vo = H.sort_ptr(b2s.b2s_radix_sort, dk, dv, kt, desc, bb, eb)
+    ek, ev = _expect(oracle, raw, vals_np, kt, desc, bb, eb)
+    got_k = H.to_np(ko, raw.dtype)
+    assert torch.equal(dk, before), f"{label}: pointer form modified its input"
+    if not np.array_equal(got_k, ek):
+        bad = np.nonzero(got_k != ek)[0]
+        raise AssertionError(f"{label}: keys differ at {bad.size} of {raw.shape[0]} positions, first {bad[:5]}")
+    if vals_np is not None:
+        got_v = vo.cpu().numpy().view(vals_np.dtype).reshape(vals_np.shape)
+        if not np.array_equal(got_v, ev):
+            bad = np.nonzero((got_v != ev).reshape(raw.shape[0], -1).any(axis=1))[0]
+            raise AssertionError(f"{label}: values differ at {bad.size} positions, first {bad[:5]}")
+
+
+def test_golden_fixtures(b2s, golden):
+    """Inputs from the reference's MT19937 stream; expected = reference harness solution."""
+    for name in golden["names"]:
+        name = str(name)
+        if name == "mt_first8":
+            continue
+        n, kb, bb, eb = (int(x) for x in golden[name + "__meta"])
+        kt = NAME_TO_TYPE[name.split("_")[0]]
+        keys = golden[name + "__keys"]
+        iota = np.arange(n, dtype=np.uint32)
+        for desc, ranks in ((False, golden[name + "__asc"]), (True, golden[name + "__desc"])):
+            ko, vo = H.sort_ptr(b2s.b2s_radix_sort, H.to_dev(keys), H.to_dev(iota), kt, desc, bb, eb)
+            assert np.array_equal(H.to_np(vo, np.uint32), ranks), f"{name} desc={desc}: ranks"
+            assert np.array_equal(H.to_np(ko, keys.dtype), keys[ranks]), f"{name} desc={desc}: keys"
+
+
+@pytest.mark.parametrize("kt", range(12))
+def test_all_key_types_vs_oracle(b2s, oracle, kt):
+    rng = np.random.default_rng(100 + kt)
+    nb = H.KEY_BYTES[kt]
+    for n in (1, 2, 33, 4097, 70001):
+        raw = H.random_bits(rng, n, nb)
+        if kt in (4, 5, 8, 11):
+            raw = H.spice_floats(raw, nb)
+        for desc in (False, True):
+            _run_and_compare(b2s, oracle, raw, None, kt, desc, label=f"{H.KEY_NAMES[kt]} n={n} keys-only desc={desc}")
+            _run_and_compare(b2s, oracle, raw, np.arange(n, dtype=np.uint32), kt, desc,
+                             label=f"{H.KEY_NAMES[kt]} n={n} pairs desc={desc}")
+
+
+@pytest.mark.parametrize("vbytes", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("kt", [6, 9, 2, 0])
+def test_value_widths(b2s, oracle, kt, vbytes):
+    rng = np.random.default_rng(vbytes * 31 + kt)
+    n = 50021
+    raw = H.random_bits(rng, n, H.KEY_BYTES[kt])
+    if vbytes == 16:
+        vals = rng.integers(0, np.iinfo(np.int64).max, size=(n, 2), dtype=np.int64).view(np.uint64)
+    else:
+        vals = H.random_bits(rng, n, vbytes)
+    _run_and_compare(b2s, oracle, raw, vals, kt, False, label=f"kt={kt} v={vbytes}")
+    _run_and_compare(b2s, oracle, raw, vals, kt, True, label=f"kt={kt} v={vbytes} desc")
+
+
+def test_edge_sizes_around_tiles(b2s, oracle):
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 31, 32, 255, 256, 257, 3071, 3072, 3073, 4095, 4096, 4097, 8191, 8192, 8193, 12288, 4096 * 5 + 17]
+    for n in sizes:
+        raw = H.random_bits(rng, n, 4)
+        if n == 0:
+            ko, vo = H.sort_ptr(b2s.b2s_radix_sort, torch.empty(0, dtype=torch.int32, device="cuda"),
+                                torch.empty(0, dtype=torch.int32, device="cuda"), 6)
+            assert ko.numel() == 0
+            continue
+        _run_and_compare(b2s, oracle, raw, np.arange(n, dtype=np.uint32), 6, False, label=f"u32/u32 n={n}")
+        _run_and_compare(b2s, oracle, raw & 0x3, None, 6, True, label=f"u32 dup-heavy n={n}")
+
+
+def test_bit_ranges_unsigned(b2s, oracle):
+    rng = np.random.default_rng(11)
+    n = 100003
+    for kt in (6, 9, 2):
+        bits = H.KEY_BYTES[kt] * 8
+        raw = H.random_bits(rng, n, H.KEY_BYTES[kt])
+        vals = np.arange(n, dtype=np.uint32)
+        for bb, eb in ((1, bits - 1), (bits // 2 - 1, bits // 2 + 1), (0, 1), (bits - 1, bits), (3, 12), (5, 5)):
+            for desc in (False, True):
+                _run_and_compare(b2s, oracle, raw, vals, kt, desc, bb, eb, label=f"kt={kt} bits=[{bb},{eb}) d={desc}")
+
+
+def test_double_buffer_semantics(b2s, oracle):
+    rng = np.random.default_rng(21)
+    n = 30011
+    for kt, eb in ((6, 32), (6, 24), (9, 64), (9, 40), (2, 16), (0, 8)):
+        raw = H.random_bits(rng, n, H.KEY_BYTES[kt])
+        vals = np.arange(n, dtype=np.uint32)
+        ek, ev = oracle.radix_sort(raw, vals, kt, False, 0, eb)
+        for selector in (0, 1):
+            kb = [torch.zeros(n, dtype=H.CONTAINER[H.KEY_BYTES[kt]], device="cuda") for _ in range(2)]
+            vb = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(2)]
+            kb[selector].copy_(H.to_dev(raw))
+            vb[selector].copy_(H.to_dev(vals))
+            ks, vs = H.sort_db(b2s.b2s_radix_sort_db, kb, vb, kt, False, 0, eb, selector=selector)
+            passes = (eb + 7) // 8
+            assert ks == vs == selector ^ (passes & 1)
+            assert np.array_equal(H.to_np(kb[ks], raw.dtype), ek)
+            assert np.array_equal(H.to_np(vb[vs], np.uint32), ev)
+        # begin_bit == end_bit: no-op, selector unchanged (dispatch_radix_sort.cuh:1945)
+        kb = [H.to_dev(raw), torch.zeros(n, dtype=H.CONTAINER[H.KEY_BYTES[kt]], device="cuda")]
+        ks, _ = H.sort_db(b2s.b2s_radix_sort_db, kb, None, kt, False, 4, 4)
+        assert ks == 0 and np.array_equal(H.to_np(kb[0], raw.dtype), raw)
+    # keys-only DoubleBuffer
+    raw = H.random_bits(rng, n, 4)
+    kb = [H.to_dev(raw), torch.zeros(n, dtype=torch.int32, device="cuda")]
+    ks, _ = H.sort_db(b2s.b2s_radix_sort_db, kb, None, 6, True)
+    assert np.array_equal(H.to_np(kb[ks], np.uint32), oracle.radix_sort(raw, None, 6, True)[0])
+
+
+def test_unaligned_pointers_and_temp(b2s, oracle):
+    """Pointers need only element alignment (reference loads are scalar); temp may be at any byte offset."""
+    rng = np.random.default_rng(31)
+    n = 20000
+    for kt, off in ((6, 1), (6, 3), (2, 1), (2, 5), (0, 7), (9, 1)):
+        nb = H.KEY_BYTES[kt]
+        raw = H.random_bits(rng, n + 8, nb)
+        vals = np.arange(n + 8, dtype=np.uint32)
+        dk, dv = H.to_dev(raw), H.to_dev(vals)
+        ko, vo = H.sort_ptr(b2s.b2s_radix_sort, dk[off:off + n], dv[1:1 + n], kt, misalign=3)
+        ek, ev = oracle.radix_sort(raw[off:off + n], vals[1:1 + n], kt)
+        assert np.array_equal(H.to_np(ko, raw.dtype), ek), (kt, off)
+        assert np.array_equal(H.to_np(vo, np.uint32), ev), (kt, off)
+
+
+def test_temp_storage_protocol(b2s):
+    n = 1 << 20
+    nbytes = ctypes.c_size_t(0)
+    # trivial problems report 1 byte (never 0) and launch nothing
+    assert b2s.b2s_radix_sort(None, ctypes.byref(nbytes), None, None, None, None, 0, 6, 0, 4, 0, 0, 32, None) == 0
+    assert nbytes.value == 1
+    assert b2s.b2s_radix_sort(None, ctypes.byref(nbytes), None, None, None, None, n, 6, 4, 4, 0, 0, 32, None) == 0
+    need = nbytes.value
+    assert need > 2 * n * 4  # pointer form carries an alternate key + value buffer
+    keys = torch.zeros(n, dtype=torch.int32, device="cuda")
+    small = ctypes.c_size_t(need - 1)
+    temp = torch.empty(need, dtype=torch.uint8, device="cuda")
+    rc = b2s.b2s_radix_sort(ctypes.c_void_p(temp.data_ptr()), ctypes.byref(small), H._p(keys), H._p(keys.clone()),
+                            H._p(keys), H._p(keys.clone()), n, 6, 4, 4, 0, 0, 32, H.stream_handle())
+    assert rc != 0, "too-small temp storage must be rejected (cudaErrorInvalidValue)"
+    assert b2s.b2s_radix_sort(None, ctypes.byref(nbytes), None, None, None, None, n, 99, 0, 4, 0, 0, 32, None) != 0
+
+
+def test_non_default_stream(b2s, oracle):
+    rng = np.random.default_rng(41)
+    raw = H.random_bits(rng, 200000, 4)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ko, _ = H.sort_ptr(b2s.b2s_radix_sort, H.to_dev(raw), None, 6)
+    assert np.array_equal(H.to_np(ko, np.uint32), oracle.radix_sort(raw, None, 6)[0])
+    assert b2s.b2s_last_launch_count() == 1 + 1 + 4  # memset + histogram + 4 digit passes
+
+
+# ---------------------------------------------------------------------------------------------
+# against the unmodified reference CUB on the same device buffers
+# ---------------------------------------------------------------------------------------------
+REF_CASES = [
+    # (key type, value bytes, log2 n, and_rounds, descending, begin_bit, end_bit)
+    (6, 0, 24, 1, False, 0, 32),    # BASELINE config 1: SortKeys u32 2^24 uniform
+    (6, 4, 22, 1, False, 0, 32),
+    (6, 4, 22, 1, True, 0, 32),
+    (9, 4, 22, 3, False, 1, 63),    # config 3 shape: u64/u32, AND-of-3, partial bits
+    (9, 4, 21, 3, False, 24, 56),
+    (9, 4, 21, 3, True, 31, 33),
+    (8, 0, 22, 1, True, 0, 32),     # config 4 shape: f32 descending with NaN / +-0 / denormals
+    (5, 0, 22, 1, True, 0, 16),     # bf16 descending
+    (4, 4, 20, 1, False, 0, 16),
+    (11, 8, 20, 1, True, 0, 64),
+    (7, 4, 20, 1, False, 0, 32),
+    (10, 0, 20, 1, True, 0, 64),
+    (0, 4, 20, 1, False, 0, 8),
+    (3, 0, 20, 1, True, 0, 16),
+    (6, 8, 20, 2, False, 0, 32),
+]
+
+
+@pytest.mark.parametrize("case", REF_CASES, ids=lambda c: f"{H.KEY_NAMES[c[0]]}_v{c[1]}_2p{c[2]}_and{c[3]}_{'desc' if c[4] else 'asc'}_{c[5]}_{c[6]}")
+def test_bit_exact_vs_reference_cub(b2s, refcub, case):
+    kt, vb, lg, rounds, desc, bb, eb = case
+    n = (1 << lg) + 12345
+    nb = H.KEY_BYTES[kt]
+    keys = H.gen_device_keys(b2s, n, nb, seed=42, and_rounds=rounds)
+    if kt in (4, 5, 8, 11):  # uniform bit patterns already contain NaN/inf/denormals; force +-0.0 as test_util.h does
+        idx = torch.arange(n, device="cuda")
+        keys[idx % 256 == 0] = 0
+        keys[idx % 256 == 1] = torch.iinfo(H.CONTAINER[nb]).min
+    vals = H.gen_device_iota(b2s, n, vb) if vb else None
+    k_ref, v_ref = H.sort_ptr(refcub.sort, keys, vals, kt, desc, bb, eb)
+    k_us, v_us = H.sort_ptr(b2s.b2s_radix_sort, keys, vals, kt, desc, bb, eb)
+    assert torch.equal(k_us, k_ref), "keys differ from reference CUB"
+    if vb:
+        assert torch.equal(v_us, v_ref), "values differ from reference CUB"
+    # DoubleBuffer form against the same answer
+    kb = [keys.clone(), torch.empty_like(keys)]
+    vbuf = [vals.clone(), torch.empty_like(vals)] if vb else None
+    ks, vs = H.sort_db(b2s.b2s_radix_sort_db, kb, vbuf, kt, desc, bb, eb)
+    assert torch.equal(kb[ks], k_ref)
+    if vb:
+        assert torch.equal(vbuf[vs], v_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: properties (+ reference CUB where memory/time allow)
+# ---------------------------------------------------------------------------------------------
+def _property_check(b2s, keys, vals, k_out, v_out, kt, desc, bb, eb):
+    inv, ksum, psum = H.check_sorted(b2s, k_out, v_out, kt, desc, bb, eb)
+    inv0, ksum0, psum0 = H.check_sorted(b2s, keys, vals, kt, desc, bb, eb)
+    assert inv == 0, f"{inv} adjacent inversions in the output"
+    assert ksum == ksum0, "key multiset changed"
+    if vals is not None:
+        assert psum == psum0, "(key,value) pairing changed"
+
+
+def test_config2_pairs_u32_2p28(b2s, refcub):
+    n = 1 << 28
+    keys = H.gen_device_keys(b2s, n, 4, seed=42)
+    vals = H.gen_device_iota(b2s, n, 4)
+    k_us, v_us = H.sort_ptr(b2s.b2s_radix_sort, keys, vals, 6)
+    _property_check(b2s, keys, vals, k_us, v_us, 6, False, 0, 32)
+    # values are source indices: gathering the input through them must reproduce the output (permutation +
+    # pairing), and equal keys must keep increasing indices (stability)
+    assert torch.equal(keys[v_us.long()], k_us)
+    same = k_us[1:] == k_us[:-1]
+    assert bool((v_us[1:][same] > v_us[:-1][same]).all()), "equal keys out of input order: not stable"
+    k_ref, v_ref = H.sort_ptr(refcub.sort, keys, vals, 6)
+    assert torch.equal(k_us, k_ref) and torch.equal(v_us, v_ref)
+
+
+def test_config3_pairs_u64_2p30_partial_bits(b2s):
+    n = 1 << 30  # exercises the 64-bit look-back words (n >= 2^30)
+    keys = H.gen_device_keys(b2s, n, 8, seed=42, and_rounds=3)
+    vals = H.gen_device_iota(b2s, n, 4)
+    kb = [keys, torch.empty_like(keys)]
+    vb = [vals, torch.empty_like(vals)]
+    inv0 = H.check_sorted(b2s, keys, vals, 9, False, 1, 63)
+    ks, vs = H.sort_db(b2s.b2s_radix_sort_db, kb, vb, 9, False, 1, 63)
+    inv = H.check_sorted(b2s, kb[ks], vb[vs], 9, False, 1, 63)
+    assert inv[0] == 0 and inv[1] == inv0[1] and inv[2] == inv0[2]
+    k_out, v_out = kb[ks], vb[vs]
+    # stability on the masked key: equal sort keys keep increasing source index
+    mask = ((1 << 62) - 1) << 1
+    mk = k_out & mask
+    same = mk[1:] == mk[:-1]
+    assert bool((v_out[1:][same] > v_out[:-1][same]).all())
+
+
+def test_config4_descending_float_2p29(b2s, refcub):
+    n = 1 << 29
+    for kt, nb in ((8, 4), (5, 2)):
+        keys = H.gen_device_keys(b2s, n, nb, seed=7)
+        idx = torch.arange(n, device="cuda")
+        keys[idx % 256 == 0] = 0
+        keys[idx % 256 == 1] = torch.iinfo(H.CONTAINER[nb]).min
+        del idx
+        k_us, _ = H.sort_ptr(b2s.b2s_radix_sort, keys, None, kt, True)
+        _property_check(b2s, keys, None, k_us, None, kt, True, 0, nb * 8)
+        k_ref, _ = H.sort_ptr(refcub.sort, keys, None, kt, True)
+        assert torch.equal(k_us, k_ref)
+        del k_us, k_ref, keys
+        torch.cuda.empty_cache()
