@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json: DeviceRadixSort::SortPairs throughput (GKeys/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+N = 1   workload = BASELINE.json configs[1]: SortPairs u32 keys / u32 values, 2^28 uniform random pairs, pointer form
+        (input never modified, so every step sorts the same unsorted input; inputs 2 GiB >> 126 MB L2).
+N > 1   the multi-GPU SortPairs (cub_b200/multi_gpu.py): 2^28 u32/u32 pairs PER GPU (weak scaling), one process per
+        GPU, globally sorted across ranks (splitter partition pass -> NCCL all-to-all -> local sort).
+One "step" = one complete sort of the batch.  `value` = pairs sorted per second over all GPUs, device-timed
+(CUDA events, max over ranks).  `e2e` = same metric through the Python mirror of cub::DeviceRadixSort with HOST
+buffers (pinned H2D + sort + D2H inside the timed region).  `roofline` = dominant kernel (one digit pass of the
+onesweep kernel): algorithmic bytes 2*(K+V)*n per launch over its CUDA-event duration, against the measured HBM
+copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` = the reference test harness' host std::stable_sort
+(oracle/host_stable_sort.cpp, restated from test/test_device_radix_sort.cu:896-956), timed on this box's cores.
+--impl reference: the reference's CPU implementation of the path (that same host stable_sort, on all host
+threads); it also reports the unmodified reference CUB 2.2.0 kernels on this GPU (oracle/_ref/libref_cub.so)
+as `reference_gpu`, the comparison north_star asks for.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KEY_TYPE_U32 = 6
+KBYTES, VBYTES, PASSES = 4, 4, 4
+ALGO_BYTES_PER_KEY = KBYTES + PASSES * 2 * (KBYTES + VBYTES)  # 68 B: SURVEY.md §8d
+PASS_BYTES_PER_KEY = 2 * (KBYTES + VBYTES)                     # one digit pass reads+writes keys and values
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference_cpu(n: int, threads: int, steps: int, warmup: int):
+    import numpy as np
+
+    from oracle import pyoracle as po
+
+    keys = np.random.default_rng(42).integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        po.host_stable_sort(keys, KEY_TYPE_U32, False, 0, 32, threads=threads)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def time_gpu_lib(fn, keys, vals, steps, warmup):
+    """Pointer-form SortPairs through a C-ABI sort function; returns (ms_per_step, keys_out, vals_out)."""
+    import torch
+
+    from tests import harness as H
+
+    n = keys.numel()
+    ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+    nbytes = ctypes.c_size_t(0)
+    args = (H._p(keys), H._p(ko), H._p(vals), H._p(vo), n, KEY_TYPE_U32, VBYTES, 4, 0, 0, 32)
+    assert fn(None, ctypes.byref(nbytes), *args, None) == 0
+    temp = torch.empty(nbytes.value, dtype=torch.uint8, device=keys.device)
+    tp = ctypes.c_void_p(temp.data_ptr())
+    s = H.stream_handle()
+    for _ in range(warmup):
+        assert fn(tp, ctypes.byref(nbytes), *args, s) == 0
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        assert fn(tp, ctypes.byref(nbytes), *args, s) == 0
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, ko, vo, temp
+
+
+def run_reference(a):
+    """Reference arm: the reference's own CPU implementation of the path (host std::stable_sort harness) on all
+    host threads; plus the unmodified reference CUB kernels on this GPU as `reference_gpu`."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+
+    threads = po.host_max_threads()
+    n = 1 << int(os.environ.get("B2S_REF_LOG2N", "25"))
+    sec = time_reference_cpu(n, threads, a.steps, a.warmup)
+    value = n / sec / 1e9
+    line = {
+        "impl": "reference", "metric": "SortPairs GKeys/s (u32 keys / u32 values)", "value": value,
+        "unit": "GKeys/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "SortPairs u32/u32 uniform random, host std::stable_sort harness of the reference "
+                               "(test/test_device_radix_sort.cu:896-956)", "n_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "GKeys/s", "cores": threads, "kind": "port",
+                         "sample": f"2^{n.bit_length() - 1} pairs per step, __gnu_parallel::stable_sort on {threads} "
+                                   "threads (the harness itself is single-threaded std::stable_sort)"},
+        "e2e": {"value": value, "unit": "GKeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            from cub_b200 import _lib
+            from tests import harness as H
+
+            ref = po.load_gpu_reference("ref")
+            if ref is not None:
+                b2s = _lib.load()  # only the input generators are used here
+                ng = 1 << int(os.environ.get("B2S_BENCH_LOG2N", "28"))
+                keys = H.gen_device_keys(b2s, ng, 4, 42)
+                vals = H.gen_device_iota(b2s, ng, 4)
+                ms, _, _, _ = time_gpu_lib(ref.sort, keys, vals, max(3, min(a.steps, 10)), 3)
+                line["reference_gpu"] = {"impl": "reference CUB 2.2.0 (Policy900 onesweep) on this GPU",
+                                         "value": ng / ms / 1e6, "unit": "GKeys/s", "ms_per_step": ms, "n": ng}
+    except Exception as e:  # noqa: BLE001
+        line["reference_gpu"] = {"unavailable": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a):
+    import torch
+
+    import cub_b200 as cb
+    from cub_b200 import _lib
+    from tests import harness as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    b2s = _lib.load()
+    n = 1 << int(os.environ.get("B2S_BENCH_LOG2N", "28"))
+    peak, peak_src = measured_peak()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    keys = H.gen_device_keys(b2s, n, 4, 42 + 1000 * rank)
+    vals = H.gen_device_iota(b2s, n, 4)
+    line = {"metric": "SortPairs GKeys/s (u32 keys / u32 values)", "unit": "GKeys/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic"}
+
+    if world == 1:
+        sampler = ClockSampler(local)
+        # ---- device-resident timing: K pointer-form sorts back to back
+        for _ in range(a.warmup):
+            pass
+        barrier()
+        sampler.start()
+        ms, ko, vo, temp = time_gpu_lib(b2s.b2s_radix_sort, keys, vals, a.steps, a.warmup)
+        clocks = sampler.stop()
+        launches_per_step = b2s.b2s_last_launch_count()
+        value = n / ms / 1e6
+        # ---- roofline leg: per-launch CUDA events inside the library, same workload
+        b2s.b2s_timing_enable(1)
+        nbytes = ctypes.c_size_t(temp.numel())
+        args = (H._p(keys), H._p(ko), H._p(vals), H._p(vo), n, KEY_TYPE_U32, VBYTES, 4, 0, 0, 32)
+        seg = (ctypes.c_float * 16)()
+        pass_ms, hist_ms, memset_ms = [], [], []
+        for _ in range(a.steps):
+            assert b2s.b2s_radix_sort(ctypes.c_void_p(temp.data_ptr()), ctypes.byref(nbytes), *args,
+                                      H.stream_handle()) == 0
+            k = b2s.b2s_timing_read(seg, 16)
+            assert k == 2 + PASSES, k
+            memset_ms.append(seg[0])
+            hist_ms.append(seg[1])
+            pass_ms.extend(seg[2:2 + PASSES])
+        b2s.b2s_timing_enable(0)
+        avg_pass = sum(pass_ms) / len(pass_ms)
+        achieved = n * PASS_BYTES_PER_KEY / avg_pass / 1e6  # GB/s
+        whole = n * ALGO_BYTES_PER_KEY / ms / 1e6
+        # ---- parity + comparator: unmodified reference CUB on the same buffers, same run
+        ref_info, parity = None, "unchecked (oracle/_ref/libref_cub.so absent)"
+        try:
+            from oracle import pyoracle as po
+
+            ref = po.load_gpu_reference("ref")
+            if ref is not None:
+                rms, rk, rv, rtemp = time_gpu_lib(ref.sort, keys, vals, max(3, min(a.steps, 10)), 3)
+                parity = "bit-exact keys+values vs reference CUB 2.2.0" if (
+                    torch.equal(rk, ko) and torch.equal(rv, vo)) else "MISMATCH vs reference CUB 2.2.0"
+                ref_info = {"impl": "reference CUB 2.2.0 (Policy900 onesweep), same GPU, same input",
+                            "value": n / rms / 1e6, "unit": "GKeys/s", "ms_per_step": rms}
+                del rk, rv, rtemp
+            tk = po.load_gpu_reference("tk")
+            if tk is not None:
+                tms, tkk, tkv, ttemp = time_gpu_lib(tk.sort, keys, vals, max(3, min(a.steps, 10)), 3)
+                line["toolkit_cub_gpu"] = {"impl": "CUDA 12.9 toolkit CUB (SM100 policy)", "value": n / tms / 1e6,
+                                           "unit": "GKeys/s", "ms_per_step": tms}
+                del tkk, tkv, ttemp
+        except Exception as e:  # noqa: BLE001
+            parity = f"reference comparison failed: {str(e)[:120]}"
+        del ko, vo, temp
+        torch.cuda.empty_cache()
+        # ---- e2e: host buffers through the Python mirror of cub::DeviceRadixSort (DoubleBuffer form)
+        h_keys = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_vals = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_keys.copy_(keys.view(torch.int32))
+        h_vals.copy_(vals.view(torch.int32))
+        sorter = cb.device_radix_sort.HostSorter(n, torch.uint32, torch.uint32, f"cuda:{local}")
+        hk, hv = h_keys.view(torch.uint32), h_vals.view(torch.uint32)
+        for _ in range(max(1, min(a.warmup, 2))):
+            sorter(hk, hv)
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(a.steps, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            sorter(hk, hv)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1) / e2e_steps
+        # ---- CPU baseline: the reference harness' single-threaded std::stable_sort on a bounded sample
+        cpu_n = 1 << int(os.environ.get("B2S_CPU_LOG2N", "25"))
+        cpu_sec = time_reference_cpu(cpu_n, 1, 1, 0)
+        line.update({
+            "value": value, "ms_per_step": ms,
+            "config": {"workload": "DeviceRadixSort::SortPairs u32 keys / u32 values, 2^%d uniform random pairs, "
+                                   "pointer form (BASELINE.json configs[1])" % (n.bit_length() - 1),
+                       "n": n, "l2": "inputs (2 GiB) larger than L2, no flush needed",
+                       "launches_per_step": f"{launches_per_step} (1 memset + 1 histogram + {PASSES} digit passes)",
+                       "parity": parity},
+            "clocks": clocks,
+            "e2e": {"value": n / e2e_ms / 1e6, "unit": "GKeys/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n * (KBYTES + VBYTES), "d2h_bytes_per_step": n * (KBYTES + VBYTES)},
+            "gpu_launches": (launches_per_step - 1) * a.steps,
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit digit pass)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n * PASS_BYTES_PER_KEY,
+                         "avg_launch_ms": avg_pass, "histogram_ms": sum(hist_ms) / len(hist_ms),
+                         "memset_ms": sum(memset_ms) / len(memset_ms),
+                         "whole_sort": {"bytes_per_key": ALGO_BYTES_PER_KEY, "achieved": whole,
+                                        "frac": whole / peak}},
+            "cpu_baseline": {"value": cpu_n / cpu_sec / 1e9, "unit": "GKeys/s", "cores": 1, "kind": "port",
+                             "sample": f"2^{cpu_n.bit_length() - 1} u32 keys + index, std::stable_sort as in "
+                                       "test/test_device_radix_sort.cu:896-956 (oracle/host_stable_sort.cpp)"},
+        })
+        if ref_info:
+            line["reference_gpu"] = ref_info
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- N > 1: multi-GPU SortPairs, weak scaling (2^28 pairs per GPU)
+    from cub_b200 import multi_gpu
+
+    sorter = multi_gpu.DistributedSorter(n, torch.uint32, torch.uint32, dist_group=None)
+    for _ in range(a.warmup):
+        sorter.sort(keys, vals)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        out = sorter.sort(keys, vals)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    ok = sorter.verify(keys, vals, out)
+    # e2e: host shards in, host shards out
+    h_keys = keys.view(torch.int32).cpu().pin_memory()
+    h_vals = vals.view(torch.int32).cpu().pin_memory()
+    barrier()
+    e0.record()
+    e2e_steps = max(1, min(a.steps, 3))
+    for _ in range(e2e_steps):
+        dk = h_keys.to("cuda", non_blocking=True).view(torch.uint32)
+        dv = h_vals.to("cuda", non_blocking=True).view(torch.uint32)
+        o = sorter.sort(dk, dv)
+        hk = o.keys.view(torch.int32).to("cpu", non_blocking=True)
+        hv = o.values.view(torch.int32).to("cpu", non_blocking=True)
+    e1.record()
+    barrier()
+    e2e = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device="cuda")
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        total = n * world
+        line.update({
+            "value": total / ms / 1e6, "ms_per_step": ms,
+            "config": {"workload": "multi-GPU SortPairs u32/u32, 2^%d uniform pairs per GPU, globally sorted across "
+                                   "ranks (splitter partition -> NCCL all-to-all -> local LSD sort)" % (n.bit_length() - 1),
+                       "n_per_gpu": n, "n_total": total, "l2": "inputs larger than L2", "verified": ok,
+                       "phases_ms": sorter.last_phase_ms()},
+            "clocks": clocks,
+            "e2e": {"value": total / float(e2e.item()) / 1e6, "unit": "GKeys/s", "ms_per_step": float(e2e.item()),
+                    "h2d_bytes_per_step": total * 8, "d2h_bytes_per_step": total * 8},
+            "gpu_launches": sorter.launches_per_sort() * a.steps * world,
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit digit pass)", "achieved": None,
+                         "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                         "note": "per-kernel roofline is reported by the N=1 run; N>1 adds NVLink all-to-all"},
+        })
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,8 @@ EXPORTS = {
     "b2s_key_bytes": (_c.c_int, [_c.c_int]),
     "b2s_version": (_c.c_char_p, []),
     "b2s_last_launch_count": (_c.c_int, []),
+    "b2s_timing_enable": (_c.c_int, [_c.c_int]),
+    "b2s_timing_read": (_c.c_int, [_c.POINTER(_c.c_float), _c.c_int]),
     "b2s_set_variant": (_c.c_int, [_c.c_int]),
     "b2s_describe_variant": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int] + [_c.POINTER(_c.c_int)] * 4),
     "b2s_lower_bound": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),

@@ -31,6 +31,18 @@ const KeyInfo kKeyInfo[B2S_KEY_TYPE_COUNT] = {
 
 thread_local int g_last_launches = 0;
 
+// Optional per-launch timing (bench.py's roofline leg): when enabled, an event is recorded on the
+// sort's stream before the first and after every enqueued operation of a sort call.
+constexpr int kMaxTimingEvents = 16;
+bool g_timing = false;
+cudaEvent_t g_events[kMaxTimingEvents] = {};
+int g_events_used = 0;
+void timing_mark(cudaStream_t s) {
+  if (!g_timing || g_events_used >= kMaxTimingEvents) return;
+  if (!g_events[g_events_used]) cudaEventCreate(&g_events[g_events_used]);
+  cudaEventRecord(g_events[g_events_used++], s);
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 DigitConsts make_consts(const KeyInfo& ki, bool descending) {
@@ -168,9 +180,12 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   unsigned char* status[2] = {base + L.off_status0, base + L.off_status1};
   const size_t osz = off64 ? 8 : 4;
 
+  g_events_used = 0;
+  timing_mark(stream);
   cudaError_t e = cudaMemsetAsync(base + L.off_ctrs, 0, L.zero_bytes, stream);
   if (e != cudaSuccess) return (int)e;
   g_last_launches++;
+  timing_mark(stream);
 
   const DigitConsts dc = make_consts(ki, descending);
 
@@ -193,6 +208,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   e = ks->hist(h, stream);
   if (e != cudaSuccess) return (int)e;
   g_last_launches++;
+  timing_mark(stream);
 
   // Ping-pong plan.  Pointer form: in -> {tmp,out} alternating so that the last pass lands in
   // `out` and `in` is only ever read.  DoubleBuffer form: the two user buffers alternate.
@@ -230,6 +246,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     e = ks->onesweep(variant, a, stream);
     if (e != cudaSuccess) return (int)e;
     g_last_launches++;
+    timing_mark(stream);
     ksrc = kdst;
     vsrc = vdst;
     cur ^= 1;
@@ -280,6 +297,26 @@ int b2s_key_bytes(int key_type) {
 const char* b2s_version(void) { return "b2s 0.1 sm_100a"; }
 
 int b2s_last_launch_count(void) { return b2s::g_last_launches; }
+
+int b2s_timing_enable(int on) {
+  const int old = b2s::g_timing;
+  b2s::g_timing = on != 0;
+  return old;
+}
+
+int b2s_timing_read(float* ms, int capacity) {
+  // segment i = time between mark i and mark i+1 of the last timed sort: [memset, histogram, pass 0, pass 1, ...]
+  const int segs = b2s::g_events_used - 1;
+  if (segs <= 0) return 0;
+  cudaError_t e = cudaEventSynchronize(b2s::g_events[b2s::g_events_used - 1]);
+  if (e != cudaSuccess) return -(int)e;
+  int i = 0;
+  for (; i < segs && i < capacity; ++i) {
+    e = cudaEventElapsedTime(&ms[i], b2s::g_events[i], b2s::g_events[i + 1]);
+    if (e != cudaSuccess) return -(int)e;
+  }
+  return i;
+}
 
 int b2s_set_variant(int variant) {
   const int old = b2s::g_variant;

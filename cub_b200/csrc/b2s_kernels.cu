@@ -26,27 +26,29 @@ constexpr int NUM_VARIANTS = 1;
 
 template <int V>
 constexpr Variant variant_cfg(int vi) {
-  // default: 256 threads, ~48 KB of staged tile, 3 CTAs/SM
-  // registers held per item across the ranking phase: key words + packed rank + value words
-  int regs_per_item = (K > 4 ? 2 : 1) + 1 + (V + 3) / 4;
-  int ipt = 48 / regs_per_item;
-  if (ipt > 16) ipt = 16;
-  if (ipt < 4) ipt = 4;
-  Variant d{256, ipt, 3, MATCH_BALLOT};
+  // registers held per item across the ranking phase: key words + packed rank (values re-use the key registers)
+  int regs_per_item = (K > 4 ? 2 : 1) + 1;
+  if ((V + 3) / 4 > (K > 4 ? 2 : 1)) regs_per_item = (V + 3) / 4 + 1;
+  int cap = 32 / regs_per_item;  // items per thread that fit a 64-register budget
+  if (cap > 16) cap = 16;
+  if (cap < 4) cap = 4;
+  // production tuning (B200 sweep, profiles/r1_tune_sweep_*.jsonl): big tiles win -- longer digit runs on
+  // the scatter side matter more than occupancy
+  Variant d = (K + V <= 8) ? Variant{512, cap, 2, MATCH_BALLOT} : Variant{384, cap > 12 ? 12 : cap, 3, MATCH_BALLOT};
 #ifdef B2S_TUNING
   switch (vi) {
     case 0: return d;
-    case 1: return Variant{256, ipt, 3, MATCH_HW};
-    case 2: return Variant{256, ipt > 12 ? 12 : ipt, 4, MATCH_BALLOT};
-    case 3: return Variant{256, ipt > 12 ? 12 : ipt, 4, MATCH_HW};
-    case 4: return Variant{384, ipt, 2, MATCH_BALLOT};
-    case 5: return Variant{384, ipt, 2, MATCH_HW};
-    case 6: return Variant{512, ipt, 2, MATCH_BALLOT};
-    case 7: return Variant{512, ipt > 12 ? 12 : ipt, 2, MATCH_BALLOT};
-    case 8: return Variant{256, ipt > 8 ? 8 : ipt, 5, MATCH_BALLOT};
-    case 9: return Variant{256, ipt + 4, 2, MATCH_BALLOT};
-    case 10: return Variant{512, ipt, 1, MATCH_BALLOT};
-    case 11: return Variant{384, ipt > 12 ? 12 : ipt, 3, MATCH_BALLOT};
+    case 1: return Variant{512, cap, 2, MATCH_BALLOT};
+    case 2: return Variant{384, cap, 3, MATCH_BALLOT};
+    case 3: return Variant{1024, cap, 1, MATCH_BALLOT};
+    case 4: return Variant{1024, cap > 12 ? 12 : cap, 1, MATCH_BALLOT};
+    case 5: return Variant{768, cap, 1, MATCH_BALLOT};
+    case 6: return Variant{512, cap + 4, 2, MATCH_BALLOT};
+    case 7: return Variant{640, cap, 1, MATCH_BALLOT};
+    case 8: return Variant{512, cap > 12 ? 12 : cap, 2, MATCH_BALLOT};
+    case 9: return Variant{384, cap > 12 ? 12 : cap, 3, MATCH_BALLOT};
+    case 10: return Variant{256, cap, 4, MATCH_BALLOT};
+    case 11: return Variant{512, cap > 8 ? 8 : cap, 3, MATCH_BALLOT};
     default: return d;
   }
 #else

@@ -157,10 +157,18 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   unsigned int* myhist = whist + warp * RADIX;
   const unsigned int myhist_s = smem_u32(myhist);
   const unsigned int lt = lanemask_lt();
+  // software-pipelined: the peer mask of row u+1 is computed before the leader atomic of row u
+  // so ballots overlap the shared-memory atomic + shuffle latency
+  unsigned int d_next = op(key[0]);
+  unsigned int m_next = MATCH == MATCH_HW ? match_hw(d_next) : match_ballot<RADIX_BITS>(d_next);
 #pragma unroll
   for (int u = 0; u < IPT; ++u) {
-    const unsigned int d = op(key[u]);
-    const unsigned int m = MATCH == MATCH_HW ? match_hw(d) : match_ballot<RADIX_BITS>(d);
+    const unsigned int d = d_next;
+    const unsigned int m = m_next;
+    if (u + 1 < IPT) {
+      d_next = op(key[u + 1]);
+      m_next = MATCH == MATCH_HW ? match_hw(d_next) : match_ballot<RADIX_BITS>(d_next);
+    }
     const unsigned int leader = bfind(m);  // highest peer lane adds the whole group
     unsigned int prev = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
     prev = __shfl_sync(0xffffffffu, prev, leader);
@@ -169,13 +177,6 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
 
   // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases
-  ValU val[HAS_VALUES ? IPT : 1];
-  if (HAS_VALUES) {
-    if (bulk) mbar_wait(&bar[1], 0);
-    const ValU* sv = reinterpret_cast<const ValU*>(stage_v + vshift);
-#pragma unroll
-    for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
-  }
   OffT* status = reinterpret_cast<OffT*>(P.status) + tile * RADIX;
   unsigned int total = 0;
   unsigned int wcnt[NW];
@@ -213,19 +214,25 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     // issue the first look-back load early; it is consumed after the shared-memory scatter
     if (tile > 0) first = ld_status(status - RADIX + tid);
   }
-  __syncthreads();  // S3: bases ready, staged values consumed
+  __syncthreads();  // S3: per-warp bases ready
 
-  // ---- P3: reorder keys and values in shared memory
+  // ---- P3: reorder keys in shared memory (staged keys were all consumed before S2)
   {
     KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
-    ValU* sv = reinterpret_cast<ValU*>(stage_v);
 #pragma unroll
     for (int u = 0; u < IPT; ++u) {
-      const unsigned int d = rk[u] >> 16;
-      const unsigned int r = (rk[u] & 0xffffu) + myhist[d];
+      const unsigned int r = (rk[u] & 0xffffu) + myhist[rk[u] >> 16];
+      rk[u] = r;
       sk[r] = (KeyU)key[u];
-      if (HAS_VALUES) sv[r] = val[u];
     }
+  }
+  // values: staged values -> registers (re-using the key registers), barrier, then in-place reorder
+  ValU val[HAS_VALUES ? IPT : 1];
+  if (HAS_VALUES) {
+    if (bulk) mbar_wait(&bar[1], 0);
+    const ValU* sv = reinterpret_cast<const ValU*>(stage_v + vshift);
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
   }
 
   // ---- look-back: exclusive prefix of this tile for digit `tid`
@@ -245,6 +252,12 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     }
     s_goff[tid] = reinterpret_cast<const OffT*>(P.bins)[tid] + excl - (OffT)tile_excl;
   }
+  if (HAS_VALUES) {
+    __syncthreads();  // S3b: every staged value is in a register
+    ValU* sv = reinterpret_cast<ValU*>(stage_v);
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) sv[rk[u]] = val[u];
+  }
   __syncthreads();  // S4
 
   // ---- P4: coalesced write-out of digit runs
@@ -253,10 +266,18 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     const ValU* sv = reinterpret_cast<const ValU*>(stage_v);
     KeyU* okeys = reinterpret_cast<KeyU*>(P.keys_out);
     ValU* ovals = reinterpret_cast<ValU*>(P.vals_out);
+    if (full) {
 #pragma unroll
-    for (int u = 0; u < IPT; ++u) {
-      const int pos = u * NT + tid;
-      if (full || pos < valid) {
+      for (int u = 0; u < IPT; ++u) {
+        const int pos = u * NT + tid;
+        const KeyU k = sk[pos];
+        const OffT dst = s_goff[op((W)k)] + (OffT)pos;
+        okeys[dst] = k;
+        if (HAS_VALUES) ovals[dst] = sv[pos];
+      }
+    } else {
+#pragma unroll 1
+      for (int pos = tid; pos < valid; pos += NT) {
         const KeyU k = sk[pos];
         const OffT dst = s_goff[op((W)k)] + (OffT)pos;
         okeys[dst] = k;

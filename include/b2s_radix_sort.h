@@ -101,6 +101,13 @@ const char *b2s_version(void);
  */
 int b2s_last_launch_count(void);
 
+/* Per-launch timing for bench.py's roofline leg (not part of the reference API).  While enabled,
+ * every sort call records CUDA events on its stream around each operation it enqueues.
+ * b2s_timing_read synchronises on the last event of the most recent call and returns the number of
+ * segments written to ms[]: [memset, histogram, digit pass 0, digit pass 1, ...] in milliseconds. */
+int b2s_timing_enable(int on);
+int b2s_timing_read(float *ms, int capacity);
+
 /* Tuning hooks (not part of the reference API).  Variant 0 is the production tuning of the
  * digit-pass kernel; a tuning build (-DB2S_TUNING) carries more points.  b2s_set_variant returns
  * the previous variant; b2s_describe_variant returns the number of variants (or -1) and the
