@@ -1,0 +1,13 @@
+import sys, json
+for l in sys.stdin:
+    try:
+        r = json.loads(l)
+    except Exception:
+        print(l.strip())
+        continue
+    m = r.get("match")
+    kind = lbw = None
+    if m is not None:
+        kind, lbw, m = (m >> 4) & 15, m >> 8, m & 15
+    print(r.get("case"), r.get("impl"), "v", r.get("variant"), r.get("nt"), r.get("ipt"), r.get("minb"), "kind", kind, "lbw", lbw,
+          round(r["gkeys_s"], 2), "GK/s", round(r["best_ms"], 3), "ms", r.get("bit_exact_vs_ref"))

@@ -29,7 +29,9 @@ template <> struct UIntOf<1> { using type = uint8_t; };
 template <> struct UIntOf<2> { using type = uint16_t; };
 template <> struct UIntOf<4> { using type = uint32_t; };
 template <> struct UIntOf<8> { using type = unsigned long long; };
-struct alignas(16) U128 { unsigned long long lo, hi; };
+// 16-byte values are opaque and only guaranteed element-aligned by the caller; 8-byte alignment keeps
+// every access legal for e.g. a struct of two doubles
+struct alignas(8) U128 { unsigned long long lo, hi; };
 template <> struct UIntOf<16> { using type = U128; };
 
 // Register-width type a key is widened to for arithmetic (8/16-bit keys compute in 32 bits).

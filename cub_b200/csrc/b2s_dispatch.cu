@@ -200,8 +200,8 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   h.done = ctrs;
   h.off64 = off64;
   {
-    const uint64_t vecs = (n * kbytes + 16 * 512 - 1) / (16 * 512);  // CTAs worth of 128-bit loads
-    uint64_t g = (uint64_t)sm_count() * 4;
+    const uint64_t vecs = (n * kbytes + 16 * 1024 - 1) / (16 * 1024);  // CTAs worth of 128-bit loads
+    uint64_t g = (uint64_t)sm_count();                                 // one 1024-thread CTA per SM
     if (g > vecs) g = vecs ? vecs : 1;
     h.grid = (int)g;
   }
@@ -331,7 +331,7 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
   if (nt) *nt = v.nt;
   if (ipt) *ipt = v.ipt;
   if (minb) *minb = v.minb;
-  if (match) *match = v.match;
+  if (match) *match = v.match | (v.kind << 4) | (v.lbw << 8);
   return ks->num_variants();
 }
 

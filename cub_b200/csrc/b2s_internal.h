@@ -47,6 +47,8 @@ struct PassArgs {
 // One tuning point of the onesweep kernel.
 struct Variant {
   int nt, ipt, minb, match;
+  int kind;  // 0: one tile per CTA (b2s_onesweep.cuh), 1: persistent pipelined (b2s_onesweep2.cuh)
+  int lbw;   // look-back window (predecessor tiles read per round trip)
 };
 
 // Implemented once per key width in b2s_kernels_k{1,2,4,8}.cu

@@ -1,10 +1,12 @@
 // b2s_kernels.cu -- kernel instantiations + launchers for ONE key width (-DB2S_K=1|2|4|8).
 // Compiled four times so the instantiations build in parallel.
+#include <cstdlib>
 #include <utility>
 
 #include "b2s_histogram.cuh"
 #include "b2s_internal.h"
 #include "b2s_onesweep.cuh"
+#include "b2s_onesweep2.cuh"
 
 #ifndef B2S_K
 #error "compile with -DB2S_K=<key bytes>"
@@ -17,38 +19,44 @@ constexpr int K = B2S_K;
 
 // ---- tuning table -------------------------------------------------------------------------
 // Variant 0 is the production tuning for (K, V).  A tuning build (-DB2S_TUNING) adds more
-// points that bench/tune.py sweeps on the GPU.
+// points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
+// with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 12;
+constexpr int NUM_VARIANTS = 14;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
 
 template <int V>
+constexpr int scale_ipt(int ipt) {
+  const int kw = K > 4 ? 2 : 1, vw = (V + 3) / 4;
+  const int regs_per_item = (vw > kw ? vw : kw) + 1;  // key words (values re-use them) + packed rank
+  const int by_bytes = (K + V <= 8) ? ipt : ipt * 8 / (K + V);
+  const int by_regs = ipt * 2 / regs_per_item;
+  const int r = by_bytes < by_regs ? by_bytes : by_regs;
+  return r < 4 ? 4 : r;
+}
+
+template <int V>
 constexpr Variant variant_cfg(int vi) {
-  // registers held per item across the ranking phase: key words + packed rank (values re-use the key registers)
-  int regs_per_item = (K > 4 ? 2 : 1) + 1;
-  if ((V + 3) / 4 > (K > 4 ? 2 : 1)) regs_per_item = (V + 3) / 4 + 1;
-  int cap = 32 / regs_per_item;  // items per thread that fit a 64-register budget
-  if (cap > 16) cap = 16;
-  if (cap < 4) cap = 4;
-  // production tuning (B200 sweep, profiles/r1_tune_sweep_*.jsonl): big tiles win -- longer digit runs on
-  // the scatter side matter more than occupancy
-  Variant d = (K + V <= 8) ? Variant{512, cap, 2, MATCH_BALLOT} : Variant{384, cap > 12 ? 12 : cap, 3, MATCH_BALLOT};
+  // {threads, items/thread, min CTAs/SM, match mode, kernel kind (0 one tile per CTA, 1 persistent), look-back window}
+  const Variant d = Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 4};
 #ifdef B2S_TUNING
   switch (vi) {
     case 0: return d;
-    case 1: return Variant{512, cap, 2, MATCH_BALLOT};
-    case 2: return Variant{384, cap, 3, MATCH_BALLOT};
-    case 3: return Variant{1024, cap, 1, MATCH_BALLOT};
-    case 4: return Variant{1024, cap > 12 ? 12 : cap, 1, MATCH_BALLOT};
-    case 5: return Variant{768, cap, 1, MATCH_BALLOT};
-    case 6: return Variant{512, cap + 4, 2, MATCH_BALLOT};
-    case 7: return Variant{640, cap, 1, MATCH_BALLOT};
-    case 8: return Variant{512, cap > 12 ? 12 : cap, 2, MATCH_BALLOT};
-    case 9: return Variant{384, cap > 12 ? 12 : cap, 3, MATCH_BALLOT};
-    case 10: return Variant{256, cap, 4, MATCH_BALLOT};
-    case 11: return Variant{512, cap > 8 ? 8 : cap, 3, MATCH_BALLOT};
+    case 1: return Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 1};
+    case 2: return Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 2};
+    case 3: return Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 8};
+    case 4: return Variant{512, scale_ipt<V>(16), 2, MATCH_BALLOT, 0, 4};
+    case 5: return Variant{384, scale_ipt<V>(16), 3, MATCH_BALLOT, 0, 4};
+    case 6: return Variant{384, scale_ipt<V>(19), 3, MATCH_BALLOT, 0, 4};
+    case 7: return Variant{512, scale_ipt<V>(22), 2, MATCH_BALLOT, 0, 4};
+    case 8: return Variant{256, scale_ipt<V>(16), 4, MATCH_BALLOT, 0, 4};
+    case 9: return Variant{256, scale_ipt<V>(20), 4, MATCH_BALLOT, 0, 4};
+    case 10: return Variant{1024, scale_ipt<V>(16), 1, MATCH_BALLOT, 0, 4};
+    case 11: return Variant{256, scale_ipt<V>(32), 2, MATCH_BALLOT, 1, 4};
+    case 12: return Variant{512, scale_ipt<V>(16), 2, MATCH_BALLOT, 1, 4};
+    case 13: return Variant{640, scale_ipt<V>(16), 1, MATCH_BALLOT, 0, 4};
     default: return d;
   }
 #else
@@ -69,16 +77,33 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   return op;
 }
 
+int sm_count_cached() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
+
 template <int V, bool F, typename OffT, int VI>
 cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   constexpr Variant c = variant_cfg<V>(VI);
-  using L = OnesweepSmem<K, V, c.nt, c.ipt>;
-  auto kern = onesweep_kernel<K, V, F, OffT, c.nt, c.ipt, c.minb, c.match>;
+  constexpr int TILE = c.nt * c.ipt;
+  constexpr int SMEM = c.kind == 1 ? Onesweep2Smem<K, V, c.nt, c.ipt>::TOTAL : OnesweepSmem<K, V, c.nt, c.ipt>::TOTAL;
+  void (*kern)(const OnesweepParams<K, F>);
+  if constexpr (c.kind == 1)
+    kern = onesweep2_kernel<K, V, F, OffT, c.nt, c.ipt, c.minb, c.lbw>;
+  else
+    kern = onesweep_kernel<K, V, F, OffT, c.nt, c.ipt, c.minb, c.lbw>;
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
@@ -93,9 +118,20 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   p.tile_counter = a.tile_counter;
   p.n = a.n;
   p.pad_key = a.dc.pad_key;
+  {
+    static const int stagger_env = [] { const char* e = std::getenv("B2S_STAGGER_NS"); return e ? std::atoi(e) : -1; }();
+    const unsigned int sms = (unsigned int)sm_count_cached();
+    p.stagger_lo = sms;
+    p.stagger_hi = c.minb > 1 ? sms * 2 : sms;
+    p.stagger_ns = stagger_env >= 0 ? (unsigned int)stagger_env : 0u;
+  }
   p.op = make_op<F>(a.dc, a.bit, a.nbits);
-  const unsigned long long tiles = (a.n + L::TILE - 1) / L::TILE;
-  kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
+  unsigned long long grid = (a.n + TILE - 1) / TILE;
+  if (c.kind == 1) {
+    const unsigned long long resident = (unsigned long long)sm_count_cached() * c.minb;
+    if (grid > resident) grid = resident;
+  }
+  kern<<<(unsigned int)grid, c.nt, SMEM, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -139,7 +175,16 @@ cudaError_t hist_one(const HistArgs& a, cudaStream_t s) {
   p.num_passes = a.num_passes;
   p.ghist = a.ghist;
   p.done = a.done;
-  histogram_kernel<K, F, OffT><<<a.grid, HIST_THREADS, 0, s>>>(p);
+  auto kern = histogram_kernel<K, F, OffT>;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HistSmem<K>::BYTES);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  kern<<<a.grid, HIST_THREADS, HistSmem<K>::BYTES, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -177,7 +222,7 @@ Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes) {
     case 4: return variant_cfg<4>(variant);
     case 8: return variant_cfg<8>(variant);
     case 16: return variant_cfg<16>(variant);
-    default: return Variant{0, 0, 0, 0};
+    default: return Variant{0, 0, 0, 0, 0, 0};
   }
 }
 

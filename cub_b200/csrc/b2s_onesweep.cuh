@@ -20,7 +20,8 @@
 //   * look-back status words are gpu-scope relaxed (not system-scope volatile), one status
 //     array per pass parity: a pass clears the NEXT pass' array, so the whole sort needs a
 //     single memset; 64-bit status words when n >= 2^30 instead of <=2^28-item portions;
-//   * the first look-back load is issued before the shared-memory scatter to hide its latency.
+//   * the look-back reads a window of LBW predecessor tiles per round trip (independent loads, issued late
+//     so that they see fresh state) instead of one.
 //
 // Stability: items are ranked in tile order (warp-striped rows, lane order inside a row,
 // rows in program order); tiles are ordered by the dynamic tile id == position in the input.
@@ -43,6 +44,8 @@ struct OnesweepParams {
   unsigned int* tile_counter;
   unsigned long long n;
   unsigned long long pad_key;  // raw key whose bit-ordered form is all ones
+  unsigned int stagger_lo, stagger_hi;  // CTAs with blockIdx in [lo, hi) start `stagger_ns` late (see kernel)
+  unsigned int stagger_ns;
   DigitOp<KBYTES, IS_FLOAT> op;
 };
 
@@ -60,7 +63,7 @@ struct OnesweepSmem {
   static constexpr int TOTAL = OFF_MISC + 128;
 };
 
-template <int KBYTES, int VBYTES, bool IS_FLOAT, typename OffT, int NT, int IPT, int MINB, int MATCH>
+template <int KBYTES, int VBYTES, bool IS_FLOAT, typename OffT, int NT, int IPT, int MINB, int LBW>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, IS_FLOAT> P) {
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
@@ -91,6 +94,11 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
 
   // ---- P0: claim a tile (launch order == input order), arm the barriers, clear counters
   if (tid == 0) {
+    // Co-resident CTAs of one SM are launched together and do identical work, so they stay in phase: all of
+    // them rank (ALU-bound) at the same time, then all of them scatter (LSU-bound).  Delaying the second
+    // first-wave CTA of every SM by about half a tile puts the pairs in anti-phase, and every later CTA
+    // inherits the offset of the slot it is launched into.  The delay comes BEFORE the tile is claimed.
+    if (blockIdx.x >= P.stagger_lo && blockIdx.x < P.stagger_hi) __nanosleep(P.stagger_ns);
     *s_tile = atomicAdd(P.tile_counter, 1u);
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -160,14 +168,14 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   // software-pipelined: the peer mask of row u+1 is computed before the leader atomic of row u
   // so ballots overlap the shared-memory atomic + shuffle latency
   unsigned int d_next = op(key[0]);
-  unsigned int m_next = MATCH == MATCH_HW ? match_hw(d_next) : match_ballot<RADIX_BITS>(d_next);
+  unsigned int m_next = match_ballot<RADIX_BITS>(d_next);
 #pragma unroll
   for (int u = 0; u < IPT; ++u) {
     const unsigned int d = d_next;
     const unsigned int m = m_next;
     if (u + 1 < IPT) {
       d_next = op(key[u + 1]);
-      m_next = MATCH == MATCH_HW ? match_hw(d_next) : match_ballot<RADIX_BITS>(d_next);
+      m_next = match_ballot<RADIX_BITS>(d_next);
     }
     const unsigned int leader = bfind(m);  // highest peer lane adds the whole group
     unsigned int prev = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
@@ -198,7 +206,6 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   if (tid < RADIX && lane == 31) s_wtot[warp] = incl;
   __syncthreads();  // S2b
   unsigned int tile_excl = 0;
-  OffT first = 0;
   if (tid < RADIX) {
     unsigned int base = 0;
 #pragma unroll
@@ -211,8 +218,6 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       whist[w * RADIX + tid] = run;
       run += wcnt[w];
     }
-    // issue the first look-back load early; it is consumed after the shared-memory scatter
-    if (tile > 0) first = ld_status(status - RADIX + tid);
   }
   __syncthreads();  // S3: per-warp bases ready
 
@@ -235,18 +240,33 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
   }
 
-  // ---- look-back: exclusive prefix of this tile for digit `tid`
+  // ---- look-back: exclusive prefix of this tile for digit `tid`.  Each round trip reads the next LBW
+  // predecessors with independent loads -- issued only now, so that they see fresh state: a predecessor
+  // publishes its inclusive prefix one round trip after ITS look-back starts, so a load issued before the
+  // scatter above would only ever see partial counts -- and sums partial counts up to the nearest
+  // inclusive prefix.  The walk takes ~ (L2 round trip)^2 / (LBW * time between consecutive tiles).
   if (tid < RADIX) {
     OffT excl = 0;
     if (tile > 0) {
-      const OffT* p = status - RADIX + tid;
-      OffT v = first;
+      const OffT* p = status - RADIX + tid;  // first entry of the current window
+      unsigned long long left = tile;        // predecessors not yet examined
+      bool done = false;
       while (true) {
-        while ((v & (FLAG_INCLUSIVE | FLAG_PARTIAL)) == 0) v = ld_status(p);
-        excl += v & VALUE_MASK;
-        if (v & FLAG_INCLUSIVE) break;
-        p -= RADIX;
-        v = ld_status(p);
+        OffT win[LBW];
+#pragma unroll
+        for (int j = 0; j < LBW; ++j) win[j] = (left > (unsigned long long)j) ? ld_status(p - j * RADIX) : FLAG_INCLUSIVE;
+#pragma unroll
+        for (int j = 0; j < LBW; ++j) {
+          if (!done) {
+            OffT v = win[j];
+            while ((v & (FLAG_INCLUSIVE | FLAG_PARTIAL)) == 0) v = ld_status(p - j * RADIX);
+            excl += v & VALUE_MASK;
+            if (v & FLAG_INCLUSIVE) done = true;
+          }
+        }
+        if (done) break;
+        p -= LBW * RADIX;
+        left -= LBW;
       }
       st_status(status + tid, FLAG_INCLUSIVE | (excl + (OffT)total));
     }
