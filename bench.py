@@ -308,7 +308,7 @@ def run_ours(a):
     # ---- N > 1: multi-GPU SortPairs, weak scaling (2^28 pairs per GPU)
     from cub_b200 import multi_gpu
 
-    sorter = multi_gpu.DistributedSorter(n, torch.uint32, torch.uint32, dist_group=None)
+    sorter = multi_gpu.DistributedSorter(n, torch.uint32, torch.uint32, exchange=os.environ.get("B2S_EXCHANGE", "auto"))
     for _ in range(a.warmup):
         sorter.sort(keys, vals)
     barrier()

@@ -59,7 +59,7 @@ struct DigitOp {
   static constexpr W ONES = KBYTES == 8 ? ~W(0) : (W)((1ull << (KBITS % 64)) - 1);
   static constexpr W HIGH = W(1) << (KBITS - 1);
 
-  __device__ __forceinline__ W ordered(W k) const {
+  __host__ __device__ __forceinline__ W ordered(W k) const {
     if (IS_FLOAT) {
       k = (k == zero_from) ? zero_to : k;
       // Traits<fp>::TwiddleIn: negative -> flip all bits, non-negative -> flip the sign bit.
@@ -70,6 +70,31 @@ struct DigitOp {
     }
   }
   __device__ __forceinline__ uint32_t operator()(W k) const { return (uint32_t)(ordered(k) >> bit) & mask; }
+};
+
+// Destination functor of the multi-GPU partition pass: "digit" = number of splitters that order at or before
+// this key, i.e. the rank the key is sent to.  Splitters are (key, source rank) pairs; a key equal to splitter
+// j goes right of it iff the splitter was sampled on a rank <= this one (`tie` bit j), which spreads long runs
+// of equal keys over several destinations without breaking stability (equal keys stay in rank order).
+template <int KBYTES, bool IS_FLOAT>
+struct SplitterOp {
+  using W = typename WideOf<KBYTES>::type;
+  static constexpr int MAX_SPLITTERS = 7;
+  DigitOp<KBYTES, IS_FLOAT> base;  // .bit = begin_bit of the sort; .mask unused
+  W range_mask;                    // ones over (end_bit - begin_bit) bits
+  W s[MAX_SPLITTERS];              // splitters in the same (ordered >> begin_bit) & range_mask form, ascending
+  uint32_t tie;                    // bit j: splitter j's source rank <= this rank
+  int count;
+
+  __host__ __device__ __forceinline__ W sort_key(W k) const { return (W)(base.ordered(k) >> base.bit) & range_mask; }
+  __device__ __forceinline__ uint32_t operator()(W k) const {
+    const W o = sort_key(k);
+    uint32_t d = 0;
+#pragma unroll
+    for (int j = 0; j < MAX_SPLITTERS; ++j)
+      if (j < count) d += (o > s[j] || (o == s[j] && ((tie >> j) & 1u))) ? 1u : 0u;
+    return d;
+  }
 };
 
 // Host-side description of a key type, resolved once per call.
@@ -172,8 +197,9 @@ __device__ __forceinline__ uint32_t match_ballot(uint32_t d) {
   if (BITS > 7) match_bit<7>(m, d);
   return m;
 }
-// Hardware MATCH.ANY variant.
-__device__ __forceinline__ uint32_t match_hw(uint32_t d) { return __match_any_sync(0xffffffffu, d); }
+// (The hardware MATCH.ANY instruction is not an option: on B200 its cost grows with the number of distinct
+// values in the warp, ~45-60 cycles per warp instruction per SM for random 8-bit digits against ~7 for the
+// eight ballot rounds above -- bench/micro/prim.cu, profiles/r1_prim_microbench.txt.)
 
 // index of the most significant set bit (SASS FLO)
 __device__ __forceinline__ uint32_t bfind(uint32_t x) {

@@ -76,12 +76,19 @@ struct KernelSet {
   int (*tile)(int, int);
   int (*num_variants)();
   Variant (*variant)(int, int);
+  cudaError_t (*split_count)(const SplitArgs&, cudaStream_t);
+  cudaError_t (*split)(const SplitArgs&, cudaStream_t);
+  int (*split_tile)(int);
 };
 const KernelSet* kernels_for(int kbytes) {
-  static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1, onesweep_variant_k1};
-  static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2, onesweep_variant_k2};
-  static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4, onesweep_variant_k4};
-  static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8, onesweep_variant_k8};
+  static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1, onesweep_variant_k1,
+                            split_count_launch_k1, split_launch_k1, split_tile_k1};
+  static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2, onesweep_variant_k2,
+                            split_count_launch_k2, split_launch_k2, split_tile_k2};
+  static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4, onesweep_variant_k4,
+                            split_count_launch_k4, split_launch_k4, split_tile_k4};
+  static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8, onesweep_variant_k8,
+                            split_count_launch_k8, split_launch_k8, split_tile_k8};
   switch (kbytes) {
     case 1: return &k1;
     case 2: return &k2;
@@ -255,10 +262,144 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   return (int)cudaSuccess;
 }
 
+
+// ---- multi-GPU partition pass ---------------------------------------------------------------------------------
+bool fill_split_args(SplitArgs& a, uint64_t n, int key_type, int vbytes, bool descending, int begin_bit, int end_bit,
+                     const void* h_splitter_keys, const int* h_splitter_ranks, int num_splitters, int my_rank) {
+  if (key_type < 0 || key_type >= B2S_KEY_TYPE_COUNT) return false;
+  if (num_splitters < 0 || num_splitters > kMaxSplitters) return false;
+  if (num_splitters && (!h_splitter_keys || !h_splitter_ranks)) return false;
+  const KeyInfo ki = kKeyInfo[key_type];
+  if (end_bit <= begin_bit || begin_bit < 0 || end_bit > ki.bytes * 8) return false;
+  a = SplitArgs{};
+  a.pass.n = n;
+  a.pass.dc = make_consts(ki, descending);
+  a.pass.bit = begin_bit;
+  a.pass.nbits = 8;
+  a.pass.off64 = true;
+  a.pass.vbytes = vbytes;
+  a.end_bit = end_bit;
+  a.num_splitters = num_splitters;
+  for (int j = 0; j < num_splitters; ++j) {
+    uint64_t k = 0;
+    std::memcpy(&k, static_cast<const unsigned char*>(h_splitter_keys) + (size_t)j * ki.bytes, ki.bytes);  // little endian
+    a.splitters[j] = k;
+    if (h_splitter_ranks[j] <= my_rank) a.tie |= 1u << j;
+  }
+  return true;
+}
+
+struct SplitLayout {
+  size_t off_ctr, off_bins, off_status, total, zero_bytes;
+};
+SplitLayout carve_split(uint64_t n, int tile) {
+  SplitLayout L{};
+  const uint64_t tiles = (n + tile - 1) / tile;
+  size_t o = 0;
+  L.off_ctr = o;    o += 256;
+  L.off_bins = o;   o += 8 * 256;
+  L.off_status = o; o += align_up(8 * 256 * tiles, 256);
+  L.zero_bytes = o;
+  L.total = o + 255;
+  return L;
+}
+
 }  // namespace
 }  // namespace b2s
 
 extern "C" {
+
+int b2s_enable_peer_access(int peer_device) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (peer_device == dev) return (int)cudaSuccess;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) return (int)e;
+  if (!can) return (int)cudaErrorPeerAccessUnsupported;
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();  // clear the sticky-free error state
+    e = cudaSuccess;
+  }
+  return (int)e;
+}
+
+int b2s_ipc_open(const void* handle64, void** d_ptr) {
+  if (!handle64 || !d_ptr) return (int)cudaErrorInvalidValue;
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(&h, handle64, sizeof(h));
+  // opened with the CURRENT device being the one whose kernels will store into the buffer, so that the driver
+  // sets up the peer mapping for it
+  return (int)cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int b2s_ipc_close(void* d_ptr) { return (int)cudaIpcCloseMemHandle(d_ptr); }
+
+int b2s_split_count(const void* d_keys_in, uint64_t num_items, int key_type, int descending, int begin_bit, int end_bit,
+                    const void* h_splitter_keys, const int* h_splitter_ranks, int num_splitters, int my_rank,
+                    uint64_t* d_counts, b2s_stream_t stream) {
+  b2s::SplitArgs a;
+  if (!d_counts || !b2s::fill_split_args(a, num_items, key_type, 0, descending != 0, begin_bit, end_bit, h_splitter_keys,
+                                         h_splitter_ranks, num_splitters, my_rank))
+    return (int)cudaErrorInvalidValue;
+  const b2s::KernelSet* ks = b2s::kernels_for(b2s::kKeyInfo[key_type].bytes);
+  cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) * (size_t)(num_splitters + 1), (cudaStream_t)stream);
+  if (e != cudaSuccess || num_items == 0) return (int)e;
+  a.pass.keys_in = d_keys_in;
+  a.counts = reinterpret_cast<uint64_t*>(d_counts);
+  return (int)ks->split_count(a, (cudaStream_t)stream);
+}
+
+int b2s_split_scatter(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, void* d_keys_out,
+                      const void* d_values_in, void* d_values_out, uint64_t num_items, int key_type, int value_bytes,
+                      int descending, int begin_bit, int end_bit, const void* h_splitter_keys,
+                      const int* h_splitter_ranks, int num_splitters, int my_rank, const uint64_t* h_dest_offsets,
+                      void* const* peer_keys, void* const* peer_vals, b2s_stream_t stream) {
+  if (!temp_storage_bytes) return (int)cudaErrorInvalidValue;
+  b2s::SplitArgs a;
+  if (!b2s::fill_split_args(a, num_items, key_type, value_bytes, descending != 0, begin_bit, end_bit, h_splitter_keys,
+                            h_splitter_ranks, num_splitters, my_rank))
+    return (int)cudaErrorInvalidValue;
+  const b2s::KernelSet* ks = b2s::kernels_for(b2s::kKeyInfo[key_type].bytes);
+  const int tile = ks->split_tile(value_bytes);
+  if (tile == 0) return (int)cudaErrorNotSupported;  // 4-/8-byte keys with 0-/4-/8-byte values only
+  if (num_items == 0) {
+    if (!d_temp_storage) *temp_storage_bytes = 1;
+    return (int)cudaSuccess;
+  }
+  const b2s::SplitLayout L = b2s::carve_split(num_items, tile);
+  if (!d_temp_storage) {
+    *temp_storage_bytes = L.total;
+    return (int)cudaSuccess;
+  }
+  if (*temp_storage_bytes < L.total || !h_dest_offsets) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* base = reinterpret_cast<unsigned char*>(b2s::align_up(reinterpret_cast<uintptr_t>(d_temp_storage), 256));
+  cudaError_t e = cudaMemsetAsync(base, 0, L.zero_bytes, s);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyAsync(base + L.off_bins, h_dest_offsets, sizeof(uint64_t) * (size_t)(num_splitters + 1),
+                      cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return (int)e;
+  a.pass.keys_in = d_keys_in;
+  a.pass.keys_out = d_keys_out;
+  a.pass.vals_in = d_values_in;
+  a.pass.vals_out = d_values_out;
+  a.pass.status = base + L.off_status;
+  a.pass.status_next = nullptr;
+  a.pass.bins = base + L.off_bins;
+  a.pass.tile_counter = reinterpret_cast<unsigned int*>(base + L.off_ctr);
+  a.peer = peer_keys != nullptr;
+  if (a.peer) {
+    for (int d = 0; d <= num_splitters; ++d) {
+      a.peer_keys[d] = peer_keys[d];
+      a.peer_vals[d] = (value_bytes && peer_vals) ? peer_vals[d] : nullptr;
+    }
+  }
+  return (int)ks->split(a, s);
+}
 
 int b2s_radix_sort(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, void* d_keys_out,
                    const void* d_values_in, void* d_values_out, uint64_t num_items, int key_type, int value_bytes,
@@ -331,7 +472,7 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
   if (nt) *nt = v.nt;
   if (ipt) *ipt = v.ipt;
   if (minb) *minb = v.minb;
-  if (match) *match = v.match | (v.kind << 4) | (v.lbw << 8);
+  if (match) *match = v.lbw << 8;  // legacy slot: look-back window in bits 8+
   return ks->num_variants();
 }
 

@@ -44,20 +44,36 @@ struct PassArgs {
   int vbytes;
 };
 
-// One tuning point of the onesweep kernel.
-struct Variant {
-  int nt, ipt, minb, match;
-  int kind;  // 0: one tile per CTA (b2s_onesweep.cuh), 1: persistent pipelined (b2s_onesweep2.cuh)
-  int lbw;   // look-back window (predecessor tiles read per round trip)
+// Multi-GPU partition pass (b2s_split): destination = number of splitters ordering at or before the key.
+constexpr int kMaxSplitters = 7;
+struct SplitArgs {
+  PassArgs pass;                     // .bit = begin_bit, .nbits unused; .bins = uint64 offsets per destination
+  int end_bit;
+  uint64_t splitters[kMaxSplitters]; // raw keys
+  uint32_t tie;                      // bit j: splitter j was sampled on a rank <= this rank
+  int num_splitters;
+  void* peer_keys[8];                // non-null => write destination d into peer_keys[d] / peer_vals[d]
+  void* peer_vals[8];
+  bool peer;
+  uint64_t* counts;                  // count launch: uint64[num_splitters + 1], zeroed by the caller
 };
 
-// Implemented once per key width in b2s_kernels_k{1,2,4,8}.cu
+// One tuning point of the digit-pass kernel.
+struct Variant {
+  int nt, ipt, minb;
+  int lbw;  // look-back window (predecessor tiles read per round trip)
+};
+
+// Implemented once per key width in b2s_kernels.cu (-DB2S_K=1|2|4|8)
 #define B2S_DECL_K(K)                                                                         \
   cudaError_t hist_launch_k##K(const HistArgs& a, cudaStream_t s);                            \
   cudaError_t onesweep_launch_k##K(int variant, const PassArgs& a, cudaStream_t s);           \
   int onesweep_tile_k##K(int variant, int vbytes);                                            \
   int onesweep_num_variants_k##K();                                                           \
-  Variant onesweep_variant_k##K(int variant, int vbytes);
+  Variant onesweep_variant_k##K(int variant, int vbytes);                                     \
+  cudaError_t split_count_launch_k##K(const SplitArgs& a, cudaStream_t s);                    \
+  cudaError_t split_launch_k##K(const SplitArgs& a, cudaStream_t s);                          \
+  int split_tile_k##K(int vbytes);
 B2S_DECL_K(1)
 B2S_DECL_K(2)
 B2S_DECL_K(4)

@@ -6,7 +6,7 @@
 #include "b2s_histogram.cuh"
 #include "b2s_internal.h"
 #include "b2s_onesweep.cuh"
-#include "b2s_onesweep2.cuh"
+#include "b2s_split.cuh"
 
 #ifndef B2S_K
 #error "compile with -DB2S_K=<key bytes>"
@@ -22,7 +22,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 14;
+constexpr int NUM_VARIANTS = 12;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -39,24 +39,24 @@ constexpr int scale_ipt(int ipt) {
 
 template <int V>
 constexpr Variant variant_cfg(int vi) {
-  // {threads, items/thread, min CTAs/SM, match mode, kernel kind (0 one tile per CTA, 1 persistent), look-back window}
-  const Variant d = Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 4};
+  // {threads, items/thread, min CTAs/SM, look-back window}.  Production point from the B200 sweeps in
+  // profiles/r1_tune_sweep_*.jsonl: big tiles win (longer digit runs on the scatter side, shorter look-back
+  // walks), two 512-thread CTAs per SM.
+  const Variant d = Variant{512, scale_ipt<V>(20), 2, 4};
 #ifdef B2S_TUNING
   switch (vi) {
     case 0: return d;
-    case 1: return Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 1};
-    case 2: return Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 2};
-    case 3: return Variant{512, scale_ipt<V>(20), 2, MATCH_BALLOT, 0, 8};
-    case 4: return Variant{512, scale_ipt<V>(16), 2, MATCH_BALLOT, 0, 4};
-    case 5: return Variant{384, scale_ipt<V>(16), 3, MATCH_BALLOT, 0, 4};
-    case 6: return Variant{384, scale_ipt<V>(19), 3, MATCH_BALLOT, 0, 4};
-    case 7: return Variant{512, scale_ipt<V>(22), 2, MATCH_BALLOT, 0, 4};
-    case 8: return Variant{256, scale_ipt<V>(16), 4, MATCH_BALLOT, 0, 4};
-    case 9: return Variant{256, scale_ipt<V>(20), 4, MATCH_BALLOT, 0, 4};
-    case 10: return Variant{1024, scale_ipt<V>(16), 1, MATCH_BALLOT, 0, 4};
-    case 11: return Variant{256, scale_ipt<V>(32), 2, MATCH_BALLOT, 1, 4};
-    case 12: return Variant{512, scale_ipt<V>(16), 2, MATCH_BALLOT, 1, 4};
-    case 13: return Variant{640, scale_ipt<V>(16), 1, MATCH_BALLOT, 0, 4};
+    case 1: return Variant{512, scale_ipt<V>(20), 2, 1};
+    case 2: return Variant{512, scale_ipt<V>(20), 2, 2};
+    case 3: return Variant{512, scale_ipt<V>(20), 2, 8};
+    case 4: return Variant{512, scale_ipt<V>(16), 2, 4};
+    case 5: return Variant{384, scale_ipt<V>(16), 3, 4};
+    case 6: return Variant{384, scale_ipt<V>(19), 3, 4};
+    case 7: return Variant{512, scale_ipt<V>(22), 2, 4};
+    case 8: return Variant{256, scale_ipt<V>(16), 4, 4};
+    case 9: return Variant{256, scale_ipt<V>(20), 4, 4};
+    case 10: return Variant{1024, scale_ipt<V>(16), 1, 4};
+    case 11: return Variant{512, scale_ipt<V>(18), 2, 4};
     default: return d;
   }
 #else
@@ -73,41 +73,24 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   op.zero_from = (W)dc.zero_from;
   op.zero_to = (W)dc.zero_to;
   op.bit = (uint32_t)bit;
-  op.mask = (1u << nbits) - 1u;
+  op.mask = nbits >= 32 ? 0xffffffffu : (1u << nbits) - 1u;
   return op;
 }
 
-int sm_count_cached() {
-  static int cached[64] = {};
+template <typename KernT>
+cudaError_t ensure_smem(KernT kern, int bytes, bool* done_per_device) {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
-  int n = 148;
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  if (n <= 0) n = 148;
-  if (dev >= 0 && dev < 64) cached[dev] = n;
-  return n;
+  if (dev < 0 || dev >= 64 || !done_per_device[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) done_per_device[dev] = true;
+  }
+  return cudaSuccess;
 }
 
-template <int V, bool F, typename OffT, int VI>
-cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
-  constexpr Variant c = variant_cfg<V>(VI);
-  constexpr int TILE = c.nt * c.ipt;
-  constexpr int SMEM = c.kind == 1 ? Onesweep2Smem<K, V, c.nt, c.ipt>::TOTAL : OnesweepSmem<K, V, c.nt, c.ipt>::TOTAL;
-  void (*kern)(const OnesweepParams<K, F>);
-  if constexpr (c.kind == 1)
-    kern = onesweep2_kernel<K, V, F, OffT, c.nt, c.ipt, c.minb, c.lbw>;
-  else
-    kern = onesweep_kernel<K, V, F, OffT, c.nt, c.ipt, c.minb, c.lbw>;
-  static bool attr_done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_done[dev] = true;
-  }
-  OnesweepParams<K, F> p;
+template <typename OpT>
+void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
   p.keys_in = a.keys_in;
   p.keys_out = a.keys_out;
   p.vals_in = a.vals_in;
@@ -118,20 +101,23 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   p.tile_counter = a.tile_counter;
   p.n = a.n;
   p.pad_key = a.dc.pad_key;
-  {
-    static const int stagger_env = [] { const char* e = std::getenv("B2S_STAGGER_NS"); return e ? std::atoi(e) : -1; }();
-    const unsigned int sms = (unsigned int)sm_count_cached();
-    p.stagger_lo = sms;
-    p.stagger_hi = c.minb > 1 ? sms * 2 : sms;
-    p.stagger_ns = stagger_env >= 0 ? (unsigned int)stagger_env : 0u;
-  }
-  p.op = make_op<F>(a.dc, a.bit, a.nbits);
-  unsigned long long grid = (a.n + TILE - 1) / TILE;
-  if (c.kind == 1) {
-    const unsigned long long resident = (unsigned long long)sm_count_cached() * c.minb;
-    if (grid > resident) grid = resident;
-  }
-  kern<<<(unsigned int)grid, c.nt, SMEM, s>>>(p);
+  p.op = op;
+  for (int i = 0; i < MAX_PEERS; ++i) p.peer_keys[i] = p.peer_vals[i] = nullptr;
+}
+
+template <int V, bool F, typename OffT, int VI>
+cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
+  constexpr Variant c = variant_cfg<V>(VI);
+  constexpr int TILE = c.nt * c.ipt;
+  using L = OnesweepSmem<K, V, c.nt, c.ipt>;
+  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false>;
+  static bool attr_done[64] = {};
+  cudaError_t e = ensure_smem(kern, L::TOTAL, attr_done);
+  if (e != cudaSuccess) return e;
+  OnesweepParams<K, DigitOp<K, F>> p;
+  fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
+  const unsigned long long tiles = (a.n + TILE - 1) / TILE;
+  kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -177,16 +163,71 @@ cudaError_t hist_one(const HistArgs& a, cudaStream_t s) {
   p.done = a.done;
   auto kern = histogram_kernel<K, F, OffT>;
   static bool attr_done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HistSmem<K>::BYTES);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_done[dev] = true;
-  }
+  cudaError_t e = ensure_smem(kern, HistSmem<K>::BYTES, attr_done);
+  if (e != cudaSuccess) return e;
   kern<<<a.grid, HIST_THREADS, HistSmem<K>::BYTES, s>>>(p);
   return cudaGetLastError();
 }
+
+// ---- multi-GPU partition pass (4- and 8-byte keys; values 0/4/8 bytes) -----------------------
+#if !defined(B2S_TUNING) && (B2S_K == 4 || B2S_K == 8)
+constexpr int SPLIT_NT = 512;
+template <int V>
+constexpr int split_ipt() { return scale_ipt<V>(16); }  // the destination functor is register-hungry
+
+template <bool F>
+SplitterOp<K, F> make_splitter_op(const SplitArgs& a) {
+  using W = typename WideOf<K>::type;
+  SplitterOp<K, F> op;
+  op.base = make_op<F>(a.pass.dc, a.pass.bit, 8);
+  const int nb = a.end_bit - a.pass.bit;
+  op.range_mask = nb >= K * 8 ? ~W(0) : (W)((W(1) << nb) - 1);
+  op.count = a.num_splitters;
+  op.tie = a.tie;
+  for (int j = 0; j < SplitterOp<K, F>::MAX_SPLITTERS; ++j)
+    op.s[j] = j < a.num_splitters ? op.sort_key((W)a.splitters[j]) : ~W(0);
+  return op;
+}
+
+template <int V, bool F, bool PEER>
+cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
+  constexpr int IPT = split_ipt<V>();
+  using L = OnesweepSmem<K, V, SPLIT_NT, IPT>;
+  using Op = SplitterOp<K, F>;
+  auto kern = onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER>;
+  static bool attr_done[64] = {};
+  cudaError_t e = ensure_smem(kern, L::TOTAL, attr_done);
+  if (e != cudaSuccess) return e;
+  OnesweepParams<K, Op> p;
+  fill_params(p, a.pass, make_splitter_op<F>(a));
+  for (int i = 0; i < MAX_PEERS; ++i) {
+    p.peer_keys[i] = a.peer_keys[i];
+    p.peer_vals[i] = a.peer_vals[i];
+  }
+  const unsigned long long tiles = (a.pass.n + L::TILE - 1) / L::TILE;
+  kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int V>
+cudaError_t split_v(const SplitArgs& a, cudaStream_t s) {
+  if (a.pass.dc.is_float)
+    return a.peer ? split_one<V, true, true>(a, s) : split_one<V, true, false>(a, s);
+  return a.peer ? split_one<V, false, true>(a, s) : split_one<V, false, false>(a, s);
+}
+
+template <bool F>
+cudaError_t split_count_one(const SplitArgs& a, cudaStream_t s) {
+  const unsigned long long per_cta = 1024ull * 16;
+  unsigned long long grid = (a.pass.n + per_cta - 1) / per_cta;
+  if (grid > 148ull * 4) grid = 148ull * 4;
+  if (grid == 0) grid = 1;
+  split_count_kernel<K, SplitterOp<K, F>><<<(unsigned int)grid, 1024, 0, s>>>(a.pass.keys_in, a.pass.n,
+                                                                            make_splitter_op<F>(a),
+                                                                            reinterpret_cast<unsigned long long*>(a.counts));
+  return cudaGetLastError();
+}
+#endif
 
 }  // namespace
 
@@ -222,7 +263,7 @@ Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes) {
     case 4: return variant_cfg<4>(variant);
     case 8: return variant_cfg<8>(variant);
     case 16: return variant_cfg<16>(variant);
-    default: return Variant{0, 0, 0, 0, 0, 0};
+    default: return Variant{0, 0, 0, 0};
   }
 }
 
@@ -232,5 +273,31 @@ int CAT(onesweep_tile_k, B2S_K)(int variant, int vbytes) {
 }
 
 int CAT(onesweep_num_variants_k, B2S_K)() { return NUM_VARIANTS; }
+
+#if !defined(B2S_TUNING) && (B2S_K == 4 || B2S_K == 8)
+cudaError_t CAT(split_count_launch_k, B2S_K)(const SplitArgs& a, cudaStream_t s) {
+  return a.pass.dc.is_float ? split_count_one<true>(a, s) : split_count_one<false>(a, s);
+}
+cudaError_t CAT(split_launch_k, B2S_K)(const SplitArgs& a, cudaStream_t s) {
+  switch (a.pass.vbytes) {
+    case 0: return split_v<0>(a, s);
+    case 4: return split_v<4>(a, s);
+    case 8: return split_v<8>(a, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+int CAT(split_tile_k, B2S_K)(int vbytes) {
+  switch (vbytes) {
+    case 0: return SPLIT_NT * split_ipt<0>();
+    case 4: return SPLIT_NT * split_ipt<4>();
+    case 8: return SPLIT_NT * split_ipt<8>();
+    default: return 0;
+  }
+}
+#else
+cudaError_t CAT(split_count_launch_k, B2S_K)(const SplitArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t CAT(split_launch_k, B2S_K)(const SplitArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+int CAT(split_tile_k, B2S_K)(int) { return 0; }
+#endif
 
 }  // namespace b2s

@@ -30,9 +30,9 @@
 
 namespace b2s {
 
-enum MatchMode { MATCH_BALLOT = 0, MATCH_HW = 1 };
+constexpr int MAX_PEERS = 8;
 
-template <int KBYTES, bool IS_FLOAT>
+template <int KBYTES, typename OpT>
 struct OnesweepParams {
   const void* keys_in;
   void* keys_out;
@@ -44,9 +44,11 @@ struct OnesweepParams {
   unsigned int* tile_counter;
   unsigned long long n;
   unsigned long long pad_key;  // raw key whose bit-ordered form is all ones
-  unsigned int stagger_lo, stagger_hi;  // CTAs with blockIdx in [lo, hi) start `stagger_ns` late (see kernel)
-  unsigned int stagger_ns;
-  DigitOp<KBYTES, IS_FLOAT> op;
+  OpT op;              // key -> digit of this pass (DigitOp), or key -> destination rank (SplitterOp)
+  // PEER launches only (multi-GPU exchange fused into the partition pass): digit d is written to
+  // peer_keys[d] / peer_vals[d] -- receive buffers of rank d mapped into this process -- instead of keys_out.
+  void* peer_keys[MAX_PEERS];
+  void* peer_vals[MAX_PEERS];
 };
 
 template <int KBYTES, int VBYTES, int NT, int IPT>
@@ -63,8 +65,8 @@ struct OnesweepSmem {
   static constexpr int TOTAL = OFF_MISC + 128;
 };
 
-template <int KBYTES, int VBYTES, bool IS_FLOAT, typename OffT, int NT, int IPT, int MINB, int LBW>
-__global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, IS_FLOAT> P) {
+template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER>
+__global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, OpT> P) {
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
   using ValU = typename UIntOf<VBYTES ? VBYTES : 1>::type;
@@ -94,11 +96,6 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
 
   // ---- P0: claim a tile (launch order == input order), arm the barriers, clear counters
   if (tid == 0) {
-    // Co-resident CTAs of one SM are launched together and do identical work, so they stay in phase: all of
-    // them rank (ALU-bound) at the same time, then all of them scatter (LSU-bound).  Delaying the second
-    // first-wave CTA of every SM by about half a tile puts the pairs in anti-phase, and every later CTA
-    // inherits the offset of the slot it is launched into.  The delay comes BEFORE the tile is claimed.
-    if (blockIdx.x >= P.stagger_lo && blockIdx.x < P.stagger_hi) __nanosleep(P.stagger_ns);
     *s_tile = atomicAdd(P.tile_counter, 1u);
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -286,23 +283,23 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     const ValU* sv = reinterpret_cast<const ValU*>(stage_v);
     KeyU* okeys = reinterpret_cast<KeyU*>(P.keys_out);
     ValU* ovals = reinterpret_cast<ValU*>(P.vals_out);
+    auto emit = [&](int pos) {
+      const KeyU k = sk[pos];
+      const unsigned int d = op((W)k);
+      const OffT dst = s_goff[d] + (OffT)pos;
+      if (PEER) {
+        okeys = reinterpret_cast<KeyU*>(P.peer_keys[d & (MAX_PEERS - 1)]);
+        ovals = reinterpret_cast<ValU*>(P.peer_vals[d & (MAX_PEERS - 1)]);
+      }
+      okeys[dst] = k;
+      if (HAS_VALUES) ovals[dst] = sv[pos];
+    };
     if (full) {
 #pragma unroll
-      for (int u = 0; u < IPT; ++u) {
-        const int pos = u * NT + tid;
-        const KeyU k = sk[pos];
-        const OffT dst = s_goff[op((W)k)] + (OffT)pos;
-        okeys[dst] = k;
-        if (HAS_VALUES) ovals[dst] = sv[pos];
-      }
+      for (int u = 0; u < IPT; ++u) emit(u * NT + tid);
     } else {
 #pragma unroll 1
-      for (int pos = tid; pos < valid; pos += NT) {
-        const KeyU k = sk[pos];
-        const OffT dst = s_goff[op((W)k)] + (OffT)pos;
-        okeys[dst] = k;
-        if (HAS_VALUES) ovals[dst] = sv[pos];
-      }
+      for (int pos = tid; pos < valid; pos += NT) emit(pos);
     }
   }
 }

@@ -40,11 +40,13 @@ def test_sass_is_sm100a_with_bulk_copy():
 
     elf = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun",
-                           "_ZN3b2s15onesweep_kernelILi4ELi4ELb0EjLi256ELi16ELi3ELi0EEEvNS_14OnesweepParamsIXT_EXT1_EEE",
-                           _lib.LIB_PATH], capture_output=True, text=True).stdout
-    if "Function" in sass:  # tuning of the default variant may rename the instantiation
-        assert "UBLKCP" in sass and "SYNCS" in sass
+    syms = subprocess.run(["cuobjdump", "-symbols", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    names = sorted({t for line in syms.splitlines() for t in line.split()
+                    if "onesweep_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEj" in t and not t.startswith("$")})
+    assert names, "production u32/u32 digit-pass kernel not found in libb2s.so"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", names[0], _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass, "digit pass must stage its tile with the TMA engine"
+    assert "VOTE" in sass and "ATOMS" in sass
 
 
 def _query(b2s, n, kt, vb, bb=0, eb=None, db=False):
