@@ -8,7 +8,9 @@
 N = 1   workload = BASELINE.json configs[1]: SortPairs u32 keys / u32 values, 2^28 uniform random pairs, pointer form
         (input never modified, so every step sorts the same unsorted input; inputs 2 GiB >> 126 MB L2).
 N > 1   the multi-GPU SortPairs (cub_b200/multi_gpu.py): 2^28 u32/u32 pairs PER GPU (weak scaling), one process per
-        GPU, globally sorted across ranks (splitter partition pass -> NCCL all-to-all -> local sort).
+        GPU, globally sorted across ranks: sampled splitters -> partition kernel that stores straight into the
+        destination ranks' receive buffers over NVLink (CUDA-IPC peer memory; B2S_EXCHANGE=nccl selects the
+        staged NCCL all-to-all instead) -> local sort.
 One "step" = one complete sort of the batch.  `value` = pairs sorted per second over all GPUs, device-timed
 (CUDA events, max over ranks).  `e2e` = same metric through the Python mirror of cub::DeviceRadixSort with HOST
 buffers (pinned H2D + sort + D2H inside the timed region).  `roofline` = dominant kernel (one digit pass of the
@@ -39,6 +41,16 @@ KEY_TYPE_U32 = 6
 KBYTES, VBYTES, PASSES = 4, 4, 4
 ALGO_BYTES_PER_KEY = KBYTES + PASSES * 2 * (KBYTES + VBYTES)  # 68 B: SURVEY.md §8d
 PASS_BYTES_PER_KEY = 2 * (KBYTES + VBYTES)                     # one digit pass reads+writes keys and values
+
+
+def ncu_traffic():
+    """DRAM bytes per digit-pass launch measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture of this workload), recorded in profiles/ncu_traffic.json with its source report."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)["onesweep_kernel_u32_u32_2p28"]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def measured_peak():
@@ -290,7 +302,7 @@ def run_ours(a):
                     "h2d_bytes_per_step": n * (KBYTES + VBYTES), "d2h_bytes_per_step": n * (KBYTES + VBYTES)},
             "gpu_launches": (launches_per_step - 1) * a.steps,
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit digit pass)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * PASS_BYTES_PER_KEY,
                          "avg_launch_ms": avg_pass, "histogram_ms": sum(hist_ms) / len(hist_ms),
                          "memset_ms": sum(memset_ms) / len(memset_ms),
@@ -342,12 +354,21 @@ def run_ours(a):
     barrier()
     e2e = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device="cuda")
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    ph = sorter.last_phase_ms()
+    nvlink = None
+    if ph.get("partition_kernel_device_ms"):
+        sent = ph["items_sent_to_peers"] * (KBYTES + VBYTES)
+        nvlink = {"kernel": "onesweep_kernel<SplitterOp, PEER> (partition fused with the all-to-all)",
+                  "bytes_sent_per_gpu": sent, "kernel_ms": ph["partition_kernel_device_ms"],
+                  "achieved": sent / ph["partition_kernel_device_ms"] / 1e6, "unit": "GB/s", "peak": 770.0,
+                  "peak_source": "B200_PROFILING.md measured peer copy, per direction"}
     if rank == 0:
         total = n * world
         line.update({
             "value": total / ms / 1e6, "ms_per_step": ms,
             "config": {"workload": "multi-GPU SortPairs u32/u32, 2^%d uniform pairs per GPU, globally sorted across "
-                                   "ranks (splitter partition -> NCCL all-to-all -> local LSD sort)" % (n.bit_length() - 1),
+                                   "ranks (sampled splitters -> partition kernel storing into peer receive buffers over "
+                                   "NVLink [exchange=%s] -> local LSD sort)" % (n.bit_length() - 1, sorter.exchange),
                        "n_per_gpu": n, "n_total": total, "l2": "inputs larger than L2", "verified": ok,
                        "phases_ms": sorter.last_phase_ms()},
             "clocks": clocks,
@@ -356,7 +377,8 @@ def run_ours(a):
             "gpu_launches": sorter.launches_per_sort() * a.steps * world,
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit digit pass)", "achieved": None,
                          "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                         "note": "per-kernel roofline is reported by the N=1 run; N>1 adds NVLink all-to-all"},
+                         "note": "per-kernel HBM roofline is reported by the N=1 run; N>1 adds the NVLink exchange",
+                         "nvlink": nvlink},
         })
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

@@ -171,7 +171,12 @@ class LocalOps:
         if temp is None or temp.numel() < nb.value:
             temp = temp_holder["split"] = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
         nb = ctypes.c_size_t(temp.numel())
+        ev = temp_holder.get("split_events")
+        if ev is None:
+            ev = temp_holder["split_events"] = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         err = self.lib.b2s_split_scatter(ctypes.c_void_p(temp.data_ptr()), ctypes.byref(nb), *common, self._stream())
+        ev[1].record()
         if err:
             raise RuntimeError(f"b2s_split_scatter failed: cudaError {err}")
         self.launches += 3
@@ -378,6 +383,10 @@ class DistributedSorter:
         t4 = time.perf_counter()
         self._phase_ms = {"splitters": (t1 - t0) * 1e3, "count+plan": (t2 - t1) * 1e3, "partition+exchange": (t3 - t2) * 1e3,
                           "local_sort": (t4 - t3) * 1e3, "exchange": self.exchange}
+        ev = self.temp.get("split_events")
+        if ev is not None:
+            self._phase_ms["partition_kernel_device_ms"] = ev[0].elapsed_time(ev[1])
+            self._phase_ms["items_sent_to_peers"] = int(send_counts.sum() - send_counts[me])
         self._launches = ops.launches - launches0
         out_k = ok[:total].view(self.key_dtype) if ok.dtype != self.key_dtype else ok[:total]
         return SortedShard(out_k, ov[:total] if ov is not None else None, total, out_counts)
