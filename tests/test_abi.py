@@ -124,3 +124,32 @@ def test_no_cpu_fallback_in_product():
                 src = open(os.path.join(root, f)).read()
                 assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src, f
                 assert "torch.sort" not in src and "argsort" not in src, f
+
+
+def _build_veneer_example():
+    import shutil
+    import subprocess
+
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = os.path.join(ROOT, "tests", "cpp", "veneer_example")
+    subprocess.check_call(["nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "veneer_example.cu"), "-L" + os.path.join(ROOT, "cub_b200"), "-lb2s",
+                           "-Xlinker", "-rpath", "-Xlinker", os.path.join(ROOT, "cub_b200"), "-o", exe])
+    return exe
+
+
+def test_cpp_veneer_call_site_compiles(b2s):
+    """A reference-style C++ call site (namespace swapped) compiles and links against the veneer + libb2s.so."""
+    assert os.path.exists(_build_veneer_example())
+
+
+@pytest.mark.gpu
+def test_cpp_veneer_call_site_runs(b2s):
+    import subprocess
+
+    exe = os.path.join(ROOT, "tests", "cpp", "veneer_example")
+    if not os.path.exists(exe):
+        exe = _build_veneer_example()
+    out = subprocess.run([exe, "300007"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "veneer example: OK" in out.stdout, out.stdout + out.stderr
