@@ -11,6 +11,6 @@ ents = re.findall(r"Compiling entry function '([^']+)'.*?\n.*?Function propertie
                   r"(\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", log)
 names = subprocess.run(["cu++filt"] + [e[0] for e in ents], capture_output=True, text=True).stdout.splitlines()
 for (name, stack, ss, sl, regs), dem in zip(ents, names):
-    m = re.search(r"(onesweep2?_kernel|histogram_kernel)<([^>]*)>", dem)
+    m = re.search(r"(onesweep\w*_kernel|histogram_kernel|split_count_kernel)<(.*)>\(", dem)
     if m and flt in m.group(2):
         print(f"{m.group(1)}<{m.group(2)}>  regs {regs} spill {ss}/{sl}")

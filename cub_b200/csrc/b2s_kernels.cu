@@ -110,13 +110,13 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   constexpr Variant c = variant_cfg<V>(VI);
   constexpr int TILE = c.nt * c.ipt;
   using L = OnesweepSmem<K, V, c.nt, c.ipt>;
-  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false>;
-  static bool attr_done[64] = {};
-  cudaError_t e = ensure_smem(kern, L::TOTAL, attr_done);
-  if (e != cudaSuccess) return e;
   OnesweepParams<K, DigitOp<K, F>> p;
   fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
   const unsigned long long tiles = (a.n + TILE - 1) / TILE;
+  static bool attr_done[64] = {};
+  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false>;
+  cudaError_t e = ensure_smem(kern, L::TOTAL, attr_done);
+  if (e != cudaSuccess) return e;
   kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
   return cudaGetLastError();
 }
