@@ -1,6 +1,8 @@
 // b2s_kernels.cu -- kernel instantiations + launchers for ONE key width (-DB2S_K=1|2|4|8).
 // Compiled four times so the instantiations build in parallel.
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <utility>
 
 #include "b2s_histogram.cuh"
@@ -77,16 +79,19 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   return op;
 }
 
+// Opt a kernel in to its dynamic shared-memory size once per (kernel, device); thread-safe.
 template <typename KernT>
-cudaError_t ensure_smem(KernT kern, int bytes, bool* done_per_device) {
+cudaError_t ensure_smem(KernT kern, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !done_per_device[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) done_per_device[dev] = true;
-  }
-  return cudaSuccess;
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.insert(key);
+  return e;
 }
 
 template <typename OpT>
@@ -113,9 +118,8 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   OnesweepParams<K, DigitOp<K, F>> p;
   fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
   const unsigned long long tiles = (a.n + TILE - 1) / TILE;
-  static bool attr_done[64] = {};
   auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false>;
-  cudaError_t e = ensure_smem(kern, L::TOTAL, attr_done);
+  cudaError_t e = ensure_smem(kern, L::TOTAL);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
   return cudaGetLastError();
@@ -161,9 +165,9 @@ cudaError_t hist_one(const HistArgs& a, cudaStream_t s) {
   p.num_passes = a.num_passes;
   p.ghist = a.ghist;
   p.done = a.done;
-  auto kern = histogram_kernel<K, F, OffT>;
-  static bool attr_done[64] = {};
-  cudaError_t e = ensure_smem(kern, HistSmem<K>::BYTES, attr_done);
+  const bool full = a.begin_bit == 0 && a.end_bit == K * 8;
+  auto kern = full ? histogram_kernel<K, F, OffT, true> : histogram_kernel<K, F, OffT, false>;
+  cudaError_t e = ensure_smem(kern, HistSmem<K>::BYTES);
   if (e != cudaSuccess) return e;
   kern<<<a.grid, HIST_THREADS, HistSmem<K>::BYTES, s>>>(p);
   return cudaGetLastError();
@@ -195,8 +199,7 @@ cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
   using L = OnesweepSmem<K, V, SPLIT_NT, IPT>;
   using Op = SplitterOp<K, F>;
   auto kern = onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER>;
-  static bool attr_done[64] = {};
-  cudaError_t e = ensure_smem(kern, L::TOTAL, attr_done);
+  cudaError_t e = ensure_smem(kern, L::TOTAL);
   if (e != cudaSuccess) return e;
   OnesweepParams<K, Op> p;
   fill_params(p, a.pass, make_splitter_op<F>(a));

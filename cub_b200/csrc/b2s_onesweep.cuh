@@ -162,23 +162,31 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   unsigned int* myhist = whist + warp * RADIX;
   const unsigned int myhist_s = smem_u32(myhist);
   const unsigned int lt = lanemask_lt();
-  // software-pipelined: the peer mask of row u+1 is computed before the leader atomic of row u
-  // so ballots overlap the shared-memory atomic + shuffle latency
-  unsigned int d_next = op(key[0]);
-  unsigned int m_next = match_ballot<RADIX_BITS>(d_next);
+  // Software pipeline over rows (a warp issues in order, so the ORDER below is what hides latency):
+  //   leader atomic of row u  ->  8 ballot rounds of row u+1 (ALU work while the atomic is in flight)
+  //   ->  rank of row u-1 from its broadcast (issued one iteration ago)  ->  SHFL broadcast of row u's atomic.
+  // Neither the ATOMS->SHFL nor the SHFL->use latency is exposed; only the shared-memory pipe's throughput is.
+  unsigned int d = op(key[0]);
+  unsigned int m = match_ballot<RADIX_BITS>(d);
+  unsigned int bcast_prev = 0, below_prev = 0, d_prev = 0;
 #pragma unroll
   for (int u = 0; u < IPT; ++u) {
-    const unsigned int d = d_next;
-    const unsigned int m = m_next;
+    const unsigned int leader = bfind(m);  // highest peer lane adds the whole group
+    const unsigned int below = __popc(m & lt);
+    const unsigned int raw = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
+    unsigned int d_next = 0, m_next = 0;
     if (u + 1 < IPT) {
       d_next = op(key[u + 1]);
       m_next = match_ballot<RADIX_BITS>(d_next);
     }
-    const unsigned int leader = bfind(m);  // highest peer lane adds the whole group
-    unsigned int prev = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
-    prev = __shfl_sync(0xffffffffu, prev, leader);
-    rk[u] = (prev + __popc(m & lt)) | (d << 16);
+    if (u > 0) rk[u - 1] = (bcast_prev + below_prev) | (d_prev << 16);
+    bcast_prev = __shfl_sync(0xffffffffu, raw, leader);
+    below_prev = below;
+    d_prev = d;
+    d = d_next;
+    m = m_next;
   }
+  rk[IPT - 1] = (bcast_prev + below_prev) | (d_prev << 16);
   __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
 
   // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases

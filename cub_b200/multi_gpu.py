@@ -137,7 +137,7 @@ class LocalOps:
         return (sp_keys, sp_ranks, sp_keys.ctypes.data_as(ctypes.c_void_p),
                 sp_ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(sp_keys.shape[0]))
 
-    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank) -> np.ndarray:
+    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank, to_host=True):
         _k, _r, pk, pr, ns = self._splitter_args(sp_keys, sp_ranks)
         counts = torch.zeros(ns + 1, dtype=torch.int64, device=self.device)
         err = self.lib.b2s_split_count(ctypes.c_void_p(keys.data_ptr()), n, key_type, int(descending), begin_bit, end_bit,
@@ -145,7 +145,7 @@ class LocalOps:
         if err:
             raise RuntimeError(f"b2s_split_count failed: cudaError {err}")
         self.launches += 2
-        return counts.cpu().numpy()
+        return counts.cpu().numpy() if to_host else counts
 
     def split_scatter(self, keys, vals, out_keys, out_vals, n, key_type, descending, begin_bit, end_bit, sp_keys,
                       sp_ranks, rank, dest_offsets: np.ndarray, peer_keys: Optional[Sequence[int]],
@@ -244,6 +244,8 @@ class DistributedSorter:
         self.samples_per_rank = samples_per_rank
         self.capacity = int(n_local * slack) + 1024
         self.temp: dict = {}
+        self._sizes_for, self._all_n = None, None
+        self._fence = self.ops.empty(1, torch.int32).zero_()
         self._phase_ms: dict = {}
         self._launches = 0
         kc, vc = _CONTAINER[self.kbytes], (value_dtype if value_dtype is not None else None)
@@ -326,10 +328,13 @@ class DistributedSorter:
         t0 = time.perf_counter()
 
         # 1. samples -> splitters (identical on every rank)
-        sizes = torch.tensor([n], dtype=torch.int64, device=self.device)
-        all_sizes = [torch.zeros_like(sizes) for _ in range(G)]
-        dist.all_gather(all_sizes, sizes, group=self.group)
-        all_n = [int(x.item()) for x in all_sizes]
+        if self._sizes_for != n:  # shard sizes are exchanged once per distinct local size (collective: all ranks re-enter)
+            sizes = torch.tensor([n], dtype=torch.int64, device=self.device)
+            all_sizes = torch.zeros(G, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(all_sizes, sizes, group=self.group)
+            self._all_n = [int(x) for x in all_sizes.cpu().tolist()]
+            self._sizes_for = n
+        all_n = self._all_n
         if min(all_n) < 1:
             raise ValueError("every rank must hold at least one item")
         s = min(self.samples_per_rank, min(all_n))
@@ -341,16 +346,17 @@ class DistributedSorter:
         sk, sr = ops.sort_db([gathered, torch.empty_like(gathered)], [src, torch.empty_like(src)], G * s, kt, desc, bb, eb,
                              self.temp)
         idx = torch.arange(1, G, device=self.device, dtype=torch.int64) * s
-        sp_keys = sk[idx].cpu().numpy().view(_NP_BITS[self.kbytes])
-        sp_ranks = sr[idx].cpu().numpy().astype(np.int32)
+        # one device->host copy for both splitter keys and their source ranks
+        packed = torch.cat([sk[idx].view(torch.uint8), sr[idx].view(torch.uint8)]).cpu().numpy()
+        sp_keys = packed[: (G - 1) * self.kbytes].view(_NP_BITS[self.kbytes]).copy()
+        sp_ranks = packed[(G - 1) * self.kbytes:].view(np.int32).copy()
         t1 = time.perf_counter()
 
         # 2. counts -> exchange plan
-        my_counts = ops.split_count(kin, n, kt, desc, bb, eb, sp_keys, sp_ranks, me)
-        cm = torch.from_numpy(my_counts.astype(np.int64)).to(self.device)
-        rows = [torch.zeros_like(cm) for _ in range(G)]
-        dist.all_gather(rows, cm, group=self.group)
-        matrix = np.stack([r.cpu().numpy() for r in rows])
+        cm = ops.split_count(kin, n, kt, desc, bb, eb, sp_keys, sp_ranks, me, to_host=False)
+        rows = ops.empty(G * G, torch.int64)
+        dist.all_gather_into_tensor(rows, cm, group=self.group)
+        matrix = rows.cpu().numpy().reshape(G, G)
         send_counts, send_offsets, recv_counts, total, peer_offsets = exchange_plan(matrix, me)
         out_counts = [int(matrix[:, d].sum()) for d in range(G)]
         if max(out_counts) > self.capacity:
@@ -359,11 +365,13 @@ class DistributedSorter:
 
         # 3. partition + exchange
         if self.exchange == "peer":
-            dist.barrier(group=self.group)  # every rank is done reading its receive buffer from the previous sort
+            # No barrier is needed BEFORE the stores: they are stream-ordered after the all_gathers above, which complete
+            # only once every peer's stream has reached them, i.e. has finished reading its receive buffer (the local
+            # sort of the previous call).  AFTER them a tiny stream-ordered all_reduce is the fence: it completes on this
+            # rank only when every rank's partition kernel -- all stores into this rank's buffer -- has completed.
             ops.split_scatter(kin, vin, None, None, n, kt, desc, bb, eb, sp_keys, sp_ranks, me, peer_offsets,
                               self.peer_k, self.peer_v if vin is not None else None, self.temp)
-            ops.synchronize()
-            dist.barrier(group=self.group)  # every rank's stores have landed
+            dist.all_reduce(self._fence, group=self.group)
         else:
             ops.split_scatter(kin, vin, self.part_k, self.part_v, n, kt, desc, bb, eb, sp_keys, sp_ranks, me,
                               send_offsets, None, None, self.temp)

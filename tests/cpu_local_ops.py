@@ -54,9 +54,10 @@ class CpuOps:
             dest[i] = sum(1 for j in range(len(sk)) if o > sk[j] or (o == sk[j] and int(sp_ranks[j]) <= rank))
         return dest
 
-    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank):
+    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank, to_host=True):
         dest = self._dest(keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank)
-        return np.bincount(dest, minlength=len(sp_keys) + 1).astype(np.uint64)
+        c = np.bincount(dest, minlength=len(sp_keys) + 1)
+        return c.astype(np.uint64) if to_host else torch.from_numpy(c.astype(np.int64))
 
     def split_scatter(self, keys, vals, out_keys, out_vals, n, key_type, descending, begin_bit, end_bit, sp_keys,
                       sp_ranks, rank, dest_offsets, peer_keys, peer_vals, temp_holder):

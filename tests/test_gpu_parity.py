@@ -289,3 +289,24 @@ def test_config4_descending_float_2p29(b2s, refcub):
         assert torch.equal(k_us, k_ref)
         del k_us, k_ref, keys
         torch.cuda.empty_cache()
+
+
+def test_more_than_2p32_items_u8(b2s):
+    """n > 2^32 (the reference tests 4 350 000 007 items, test_device_radix_sort.cu:1694-1717): 64-bit num_items, 64-bit
+    look-back words and offsets beyond 32 bits.  u8 keys keep it to one digit pass over 2 x 4.3 GB."""
+    n = (1 << 32) + 100_003
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * n + (2 << 30):
+        pytest.skip("not enough device memory")
+    keys = torch.empty(n, dtype=torch.int8, device="cuda")
+    assert b2s.b2s_fill_keys(ctypes.c_void_p(keys.data_ptr()), n, 1, 99, 1, 0, H.stream_handle()) == 0
+    out, _ = H.sort_ptr(b2s.b2s_radix_sort, keys, None, 0, n=n)
+    inv, ksum, _ = H.check_sorted(b2s, out, None, 0)
+    _inv0, ksum0, _ = H.check_sorted(b2s, keys, None, 0)
+    assert inv == 0 and ksum == ksum0
+    # exact multiset: per-value counts of input and output agree (with zero inversions this IS the sorted input)
+    def hist(t):
+        return torch.stack([t[i: i + (1 << 28)].view(torch.uint8).to(torch.int16).bincount(minlength=256)
+                            for i in range(0, n, 1 << 28)]).sum(0)
+    assert torch.equal(hist(keys), hist(out))
+    assert int(out.view(torch.uint8)[0]) == 0 and int(out.view(torch.uint8)[n - 1]) == 255
