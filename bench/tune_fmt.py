@@ -8,6 +8,6 @@ for l in sys.stdin:
     m = r.get("match")
     kind = lbw = None
     if m is not None:
-        kind, lbw, m = (m >> 4) & 15, m >> 8, m & 15
-    print(r.get("case"), r.get("impl"), "v", r.get("variant"), r.get("nt"), r.get("ipt"), r.get("minb"), "kind", kind, "lbw", lbw,
+        kind, lbw, m = m >> 16, (m >> 8) & 255, m & 15
+    print(r.get("case"), r.get("impl"), "v", r.get("variant"), r.get("nt"), r.get("ipt"), r.get("minb"), "abl", kind, "lbw", lbw,
           round(r["gkeys_s"], 2), "GK/s", round(r["best_ms"], 3), "ms", r.get("bit_exact_vs_ref"))

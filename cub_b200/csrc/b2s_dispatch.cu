@@ -472,7 +472,7 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
   if (nt) *nt = v.nt;
   if (ipt) *ipt = v.ipt;
   if (minb) *minb = v.minb;
-  if (match) *match = v.lbw << 8;  // legacy slot: look-back window in bits 8+
+  if (match) *match = (v.lbw << 8) | (v.abl << 16);  // legacy slot: look-back window in bits 8+, ablation in 16+
   return ks->num_variants();
 }
 

@@ -62,6 +62,7 @@ struct SplitArgs {
 struct Variant {
   int nt, ipt, minb;
   int lbw;  // look-back window (predecessor tiles read per round trip)
+  int abl;  // tuning builds only: timing ablation switches (0 in every product variant)
 };
 
 // Implemented once per key width in b2s_kernels.cu (-DB2S_K=1|2|4|8)

@@ -24,7 +24,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 12;
+constexpr int NUM_VARIANTS = 18;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -59,6 +59,13 @@ constexpr Variant variant_cfg(int vi) {
     case 9: return Variant{256, scale_ipt<V>(20), 4, 4};
     case 10: return Variant{1024, scale_ipt<V>(16), 1, 4};
     case 11: return Variant{512, scale_ipt<V>(18), 2, 4};
+    // timing-only ablations of the production point (wrong results by design): see ABL in b2s_onesweep.cuh
+    case 12: return Variant{512, scale_ipt<V>(20), 2, 4, 1};
+    case 13: return Variant{512, scale_ipt<V>(20), 2, 4, 2};
+    case 14: return Variant{512, scale_ipt<V>(20), 2, 4, 4};
+    case 15: return Variant{512, scale_ipt<V>(20), 2, 4, 8};
+    case 16: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 2};
+    case 17: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 8};
     default: return d;
   }
 #else
@@ -118,7 +125,7 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   OnesweepParams<K, DigitOp<K, F>> p;
   fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
   const unsigned long long tiles = (a.n + TILE - 1) / TILE;
-  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false>;
+  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false, c.abl>;
   cudaError_t e = ensure_smem(kern, L::TOTAL);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
@@ -266,7 +273,7 @@ Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes) {
     case 4: return variant_cfg<4>(variant);
     case 8: return variant_cfg<8>(variant);
     case 16: return variant_cfg<16>(variant);
-    default: return Variant{0, 0, 0, 0};
+    default: return Variant{0, 0, 0, 0, 0};
   }
 }
 

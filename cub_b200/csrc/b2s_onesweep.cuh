@@ -65,7 +65,9 @@ struct OnesweepSmem {
   static constexpr int TOTAL = OFF_MISC + 128;
 };
 
-template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER>
+// ABL: timing-only ablation switches for bench/tune.py (results are WRONG when non-zero; never used by the product):
+//   1 = no global stores in P4, 2 = no P4 at all, 4 = no ranking sweep, 8 = no look-back walk, 16 = no P3/P4 value path
+template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, OpT> P) {
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
@@ -169,8 +171,13 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   unsigned int d = op(key[0]);
   unsigned int m = match_ballot<RADIX_BITS>(d);
   unsigned int bcast_prev = 0, below_prev = 0, d_prev = 0;
+  if (ABL & 4) {
 #pragma unroll
-  for (int u = 0; u < IPT; ++u) {
+    for (int u = 0; u < IPT; ++u) rk[u] = (unsigned int)(u * 32 + lane) | (op(key[u]) << 16);
+    if (lane == 0) myhist[0] = 32 * IPT;  // keep the tile total consistent: everything counted as digit 0
+  }
+#pragma unroll
+  for (int u = 0; u < ((ABL & 4) ? 0 : IPT); ++u) {
     const unsigned int leader = bfind(m);  // highest peer lane adds the whole group
     const unsigned int below = __popc(m & lt);
     const unsigned int raw = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     d = d_next;
     m = m_next;
   }
-  rk[IPT - 1] = (bcast_prev + below_prev) | (d_prev << 16);
+  if (!(ABL & 4)) rk[IPT - 1] = (bcast_prev + below_prev) | (d_prev << 16);
   __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
 
   // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   // inclusive prefix.  The walk takes ~ (L2 round trip)^2 / (LBW * time between consecutive tiles).
   if (tid < RADIX) {
     OffT excl = 0;
-    if (tile > 0) {
+    if (tile > 0 && !(ABL & 8)) {
       const OffT* p = status - RADIX + tid;  // first entry of the current window
       unsigned long long left = tile;        // predecessors not yet examined
       bool done = false;
@@ -299,9 +306,14 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
         okeys = reinterpret_cast<KeyU*>(P.peer_keys[d & (MAX_PEERS - 1)]);
         ovals = reinterpret_cast<ValU*>(P.peer_vals[d & (MAX_PEERS - 1)]);
       }
-      okeys[dst] = k;
-      if (HAS_VALUES) ovals[dst] = sv[pos];
+      if (ABL & 1) {
+        if (dst == (OffT)0xfffffff1u) okeys[0] = k + (KeyU)(HAS_VALUES ? *reinterpret_cast<const unsigned char*>(&sv[pos]) : 0);
+        return;
+      }
+      okeys[(ABL & 4) ? dst % (OffT)P.n : dst] = k;
+      if (HAS_VALUES) ovals[(ABL & 4) ? dst % (OffT)P.n : dst] = sv[pos];
     };
+    if (ABL & 2) return;
     if (full) {
 #pragma unroll
       for (int u = 0; u < IPT; ++u) emit(u * NT + tid);
