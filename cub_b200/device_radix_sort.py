@@ -232,38 +232,81 @@ def sort_keys(keys: torch.Tensor, descending: bool = False, begin_bit: int = 0, 
 
 class HostSorter:
     """End-to-end path with HOST buffers: pinned host -> device, DoubleBuffer sort, device -> pinned host.
-    Device buffers and temp storage are allocated once and reused (what a caller of the C-ABI does)."""
+    Device buffers, temp storage and pinned result buffers are allocated once and reused (what a caller of the
+    C-ABI does).  With ``depth > 1`` consecutive calls are pipelined over three streams (upload / sort / download) and
+    ``depth`` buffer sets, so the upload of call i+1 overlaps the download of call i (PCIe is full duplex); every call
+    still uploads its own inputs and downloads its own results.  A call returns its slot's pinned result tensors, valid
+    after ``synchronize()`` (or after ``depth`` further calls have been waited for, see ``__call__``)."""
 
     def __init__(self, n: int, key_dtype: torch.dtype, value_dtype: Optional[torch.dtype], device="cuda:0",
-                 descending: bool = False, begin_bit: int = 0, end_bit: Optional[int] = None):
-        self.n, self.descending, self.begin_bit, self.end_bit = n, descending, begin_bit, end_bit
-        dev = torch.device(device)
-        self.k = [torch.empty(n, dtype=key_dtype, device=dev) for _ in range(2)]
-        self.v = [torch.empty(n, dtype=value_dtype, device=dev) for _ in range(2)] if value_dtype is not None else None
-        self.h_keys_out = torch.empty(n, dtype=key_dtype).pin_memory()
-        self.h_vals_out = torch.empty(n, dtype=value_dtype).pin_memory() if value_dtype is not None else None
+                 descending: bool = False, begin_bit: int = 0, end_bit: Optional[int] = None, depth: int = 1):
+        self.n, self.descending, self.begin_bit, self.end_bit, self.depth = n, descending, begin_bit, end_bit, depth
+        dev = self.device = torch.device(device)
         self._fn = (DeviceRadixSort.SortPairsDescending if descending else DeviceRadixSort.SortPairs) \
             if value_dtype is not None else \
             (DeviceRadixSort.SortKeysDescending if descending else DeviceRadixSort.SortKeys)
-        dk, dv = DoubleBuffer(self.k[0], self.k[1]), (DoubleBuffer(self.v[0], self.v[1]) if self.v else None)
-        args = (dk, dv, n) if self.v else (dk, n)
+        self.slots = []
+        for _ in range(depth):
+            k = [torch.empty(n, dtype=key_dtype, device=dev) for _ in range(2)]
+            v = [torch.empty(n, dtype=value_dtype, device=dev) for _ in range(2)] if value_dtype is not None else None
+            self.slots.append({"k": k, "v": v, "hk": torch.empty(n, dtype=key_dtype).pin_memory(),
+                               "hv": torch.empty(n, dtype=value_dtype).pin_memory() if value_dtype is not None else None,
+                               "done": torch.cuda.Event()})
+        s0 = self.slots[0]
+        dk, dv = DoubleBuffer(*s0["k"]), (DoubleBuffer(*s0["v"]) if s0["v"] else None)
+        args = (dk, dv, n) if dv is not None else (dk, n)
         err, self.temp_bytes = self._fn(None, 0, *args, begin_bit=begin_bit, end_bit=end_bit)
         _check(err, "temp-storage query")
-        self.temp = torch.empty(self.temp_bytes, dtype=torch.uint8, device=dev)
+        self.temp = torch.empty(self.temp_bytes, dtype=torch.uint8, device=dev)  # sorts are serialised on one stream
+        self.s_up, self.s_sort, self.s_down = (torch.cuda.Stream(dev) for _ in range(3)) if depth > 1 else (None,) * 3
+        self._calls = 0
+        # compatibility with the single-slot attribute names
+        self.h_keys_out, self.h_vals_out = s0["hk"], s0["hv"]
+
+    def _sort(self, slot, stream):
+        dk = DoubleBuffer(*slot["k"])
+        dv = DoubleBuffer(*slot["v"]) if slot["v"] else None
+        args = (dk, dv, self.n) if dv is not None else (dk, self.n)
+        err, _ = self._fn(self.temp, self.temp_bytes, *args, begin_bit=self.begin_bit, end_bit=self.end_bit, stream=stream)
+        _check(err, "radix sort")
+        return dk.Current(), (dv.Current() if dv is not None else None)
 
     def __call__(self, h_keys: torch.Tensor, h_values: Optional[torch.Tensor]):
-        self.k[0].copy_(h_keys, non_blocking=True)
-        if self.v:
-            self.v[0].copy_(h_values, non_blocking=True)
-        dk = DoubleBuffer(self.k[0], self.k[1])
-        dv = DoubleBuffer(self.v[0], self.v[1]) if self.v else None
-        args = (dk, dv, self.n) if self.v else (dk, self.n)
-        err, _ = self._fn(self.temp, self.temp_bytes, *args, begin_bit=self.begin_bit, end_bit=self.end_bit)
-        _check(err, "radix sort")
-        self.h_keys_out.copy_(dk.Current(), non_blocking=True)
-        if self.v:
-            self.h_vals_out.copy_(dv.Current(), non_blocking=True)
-        return self.h_keys_out, self.h_vals_out
+        slot = self.slots[self._calls % self.depth]
+        self._calls += 1
+        if self.depth == 1:
+            slot["k"][0].copy_(h_keys, non_blocking=True)
+            if slot["v"]:
+                slot["v"][0].copy_(h_values, non_blocking=True)
+            ok, ov = self._sort(slot, None)
+            slot["hk"].copy_(ok, non_blocking=True)
+            if ov is not None:
+                slot["hv"].copy_(ov, non_blocking=True)
+            return slot["hk"], slot["hv"]
+        slot["done"].synchronize()  # the slot's previous results have been downloaded (and may now be overwritten)
+        with torch.cuda.stream(self.s_up):
+            slot["k"][0].copy_(h_keys, non_blocking=True)
+            if slot["v"]:
+                slot["v"][0].copy_(h_values, non_blocking=True)
+            up = self.s_up.record_event()
+        self.s_sort.wait_event(up)
+        with torch.cuda.stream(self.s_sort):
+            ok, ov = self._sort(slot, self.s_sort)
+            sorted_ev = self.s_sort.record_event()
+        self.s_down.wait_event(sorted_ev)
+        with torch.cuda.stream(self.s_down):
+            slot["hk"].copy_(ok, non_blocking=True)
+            if ov is not None:
+                slot["hv"].copy_(ov, non_blocking=True)
+            slot["done"].record(self.s_down)
+        return slot["hk"], slot["hv"]
+
+    def synchronize(self):
+        if self.depth == 1:
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            for s in (self.s_up, self.s_sort, self.s_down):
+                s.synchronize()
 
 
 def sort_pairs_host(h_keys: torch.Tensor, h_values: Optional[torch.Tensor], descending: bool = False,

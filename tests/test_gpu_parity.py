@@ -310,3 +310,38 @@ def test_more_than_2p32_items_u8(b2s):
                             for i in range(0, n, 1 << 28)]).sum(0)
     assert torch.equal(hist(keys), hist(out))
     assert int(out.view(torch.uint8)[0]) == 0 and int(out.view(torch.uint8)[n - 1]) == 255
+
+
+@pytest.mark.parametrize("depth", [1, 2])
+def test_host_sorter_pipeline(oracle, depth):
+    """HostSorter (the e2e path of bench.py): host buffers in, host buffers out; with depth 2 consecutive calls are
+    pipelined over three streams and two buffer sets -- every call must still return ITS OWN sorted data."""
+    from cub_b200.device_radix_sort import HostSorter
+
+    n = 300_007
+    rng = np.random.default_rng(17)
+    sorter = HostSorter(n, torch.uint32, torch.uint32, "cuda:0", depth=depth)
+    inputs, outputs = [], []
+    for i in range(5):
+        k = H.random_bits(rng, n, 4)
+        v = np.arange(n, dtype=np.uint32) + np.uint32(i)
+        hk = torch.from_numpy(k.view(np.int32).copy()).pin_memory().view(torch.uint32)
+        hv = torch.from_numpy(v.view(np.int32).copy()).pin_memory().view(torch.uint32)
+        ok, ov = sorter(hk, hv)
+        if depth == 1:
+            sorter.synchronize()
+            outputs.append((ok.view(torch.int32).numpy().view(np.uint32).copy(), ov.view(torch.int32).numpy().view(np.uint32).copy()))
+        else:
+            outputs.append((ok, ov))
+        inputs.append((k, v, hk, hv))
+        if depth == 2 and i >= 1:  # the slot of call i-1 is only reused by call i+1: read it after its own download
+            pk, pv = outputs[i - 1]
+            sorter.slots[(i - 1) % 2]["done"].synchronize()
+            outputs[i - 1] = (pk.view(torch.int32).numpy().view(np.uint32).copy(), pv.view(torch.int32).numpy().view(np.uint32).copy())
+    sorter.synchronize()
+    if depth == 2:
+        pk, pv = outputs[-1]
+        outputs[-1] = (pk.view(torch.int32).numpy().view(np.uint32).copy(), pv.view(torch.int32).numpy().view(np.uint32).copy())
+    for (k, v, _hk, _hv), (gk, gv) in zip(inputs, outputs):
+        ek, ev = oracle.radix_sort(k, v, 6)
+        assert np.array_equal(gk, ek) and np.array_equal(gv, ev)
