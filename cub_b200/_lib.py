@@ -41,11 +41,11 @@ EXPORTS = {
     "b2s_ipc_open": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "b2s_ipc_close": (_c.c_int, [_c.c_void_p]),
     "b2s_split_count": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
-                                   _c.POINTER(_c.c_int), _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+                                   _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "b2s_split_scatter": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_size_t), _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                      _c.c_void_p, _c.c_uint64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                     _c.c_void_p, _c.POINTER(_c.c_int), _c.c_int, _c.c_int, _c.POINTER(_c.c_uint64),
-                                     _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.c_void_p]),
+                                     _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                     _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.c_uint64, _c.c_void_p]),
     "b2s_lower_bound": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "b2s_fill_keys": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_void_p]),
     "b2s_fill_iota": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_uint64, _c.c_void_p]),

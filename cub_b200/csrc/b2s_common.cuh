@@ -59,6 +59,7 @@ struct DigitOp {
   static constexpr W ONES = KBYTES == 8 ? ~W(0) : (W)((1ull << (KBITS % 64)) - 1);
   static constexpr W HIGH = W(1) << (KBITS - 1);
 
+  __device__ __forceinline__ void prepare() {}
   __host__ __device__ __forceinline__ W ordered(W k) const {
     if (IS_FLOAT) {
       k = (k == zero_from) ? zero_to : k;
@@ -79,14 +80,31 @@ struct DigitOp {
 template <int KBYTES, bool IS_FLOAT>
 struct SplitterOp {
   using W = typename WideOf<KBYTES>::type;
+  using KeyU = typename UIntOf<KBYTES>::type;
   static constexpr int MAX_SPLITTERS = 7;
   DigitOp<KBYTES, IS_FLOAT> base;  // .bit = begin_bit of the sort; .mask unused
   W range_mask;                    // ones over (end_bit - begin_bit) bits
-  W s[MAX_SPLITTERS];              // splitters in the same (ordered >> begin_bit) & range_mask form, ascending
-  uint32_t tie;                    // bit j: splitter j's source rank <= this rank
+  const void* d_keys;              // DEVICE: `count` raw splitter keys, ascending in sort order
+  const int* d_ranks;              // DEVICE: source rank of every splitter
+  int my_rank;
   int count;
+  W s[MAX_SPLITTERS];              // filled by prepare(): splitters as (ordered >> begin_bit) & range_mask
+  uint32_t tie;                    // filled by prepare(): bit j = splitter j's source rank <= this rank
 
-  __host__ __device__ __forceinline__ W sort_key(W k) const { return (W)(base.ordered(k) >> base.bit) & range_mask; }
+  __device__ __forceinline__ W sort_key(W k) const { return (W)(base.ordered(k) >> base.bit) & range_mask; }
+  // Splitters live in device memory (they come out of a device-side sort of the samples), so that the host never
+  // has to wait for them; every thread reads the <= 7 of them once (L2 hits).
+  __device__ __forceinline__ void prepare() {
+    tie = 0;
+#pragma unroll
+    for (int j = 0; j < MAX_SPLITTERS; ++j) {
+      s[j] = ~W(0);
+      if (j < count) {
+        s[j] = sort_key((W)reinterpret_cast<const KeyU*>(d_keys)[j]);
+        tie |= (d_ranks[j] <= my_rank ? 1u : 0u) << j;
+      }
+    }
+  }
   __device__ __forceinline__ uint32_t operator()(W k) const {
     const W o = sort_key(k);
     uint32_t d = 0;

@@ -265,10 +265,10 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
 
 // ---- multi-GPU partition pass ---------------------------------------------------------------------------------
 bool fill_split_args(SplitArgs& a, uint64_t n, int key_type, int vbytes, bool descending, int begin_bit, int end_bit,
-                     const void* h_splitter_keys, const int* h_splitter_ranks, int num_splitters, int my_rank) {
+                     const void* d_splitter_keys, const int* d_splitter_ranks, int num_splitters, int my_rank) {
   if (key_type < 0 || key_type >= B2S_KEY_TYPE_COUNT) return false;
   if (num_splitters < 0 || num_splitters > kMaxSplitters) return false;
-  if (num_splitters && (!h_splitter_keys || !h_splitter_ranks)) return false;
+  if (num_splitters && (!d_splitter_keys || !d_splitter_ranks)) return false;
   const KeyInfo ki = kKeyInfo[key_type];
   if (end_bit <= begin_bit || begin_bit < 0 || end_bit > ki.bytes * 8) return false;
   a = SplitArgs{};
@@ -280,12 +280,9 @@ bool fill_split_args(SplitArgs& a, uint64_t n, int key_type, int vbytes, bool de
   a.pass.vbytes = vbytes;
   a.end_bit = end_bit;
   a.num_splitters = num_splitters;
-  for (int j = 0; j < num_splitters; ++j) {
-    uint64_t k = 0;
-    std::memcpy(&k, static_cast<const unsigned char*>(h_splitter_keys) + (size_t)j * ki.bytes, ki.bytes);  // little endian
-    a.splitters[j] = k;
-    if (h_splitter_ranks[j] <= my_rank) a.tie |= 1u << j;
-  }
+  a.d_splitter_keys = d_splitter_keys;
+  a.d_splitter_ranks = d_splitter_ranks;
+  a.my_rank = my_rank;
   return true;
 }
 
@@ -339,11 +336,11 @@ int b2s_ipc_open(const void* handle64, void** d_ptr) {
 int b2s_ipc_close(void* d_ptr) { return (int)cudaIpcCloseMemHandle(d_ptr); }
 
 int b2s_split_count(const void* d_keys_in, uint64_t num_items, int key_type, int descending, int begin_bit, int end_bit,
-                    const void* h_splitter_keys, const int* h_splitter_ranks, int num_splitters, int my_rank,
+                    const void* d_splitter_keys, const int* d_splitter_ranks, int num_splitters, int my_rank,
                     uint64_t* d_counts, b2s_stream_t stream) {
   b2s::SplitArgs a;
-  if (!d_counts || !b2s::fill_split_args(a, num_items, key_type, 0, descending != 0, begin_bit, end_bit, h_splitter_keys,
-                                         h_splitter_ranks, num_splitters, my_rank))
+  if (!d_counts || !b2s::fill_split_args(a, num_items, key_type, 0, descending != 0, begin_bit, end_bit, d_splitter_keys,
+                                         d_splitter_ranks, num_splitters, my_rank))
     return (int)cudaErrorInvalidValue;
   const b2s::KernelSet* ks = b2s::kernels_for(b2s::kKeyInfo[key_type].bytes);
   cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) * (size_t)(num_splitters + 1), (cudaStream_t)stream);
@@ -355,13 +352,13 @@ int b2s_split_count(const void* d_keys_in, uint64_t num_items, int key_type, int
 
 int b2s_split_scatter(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, void* d_keys_out,
                       const void* d_values_in, void* d_values_out, uint64_t num_items, int key_type, int value_bytes,
-                      int descending, int begin_bit, int end_bit, const void* h_splitter_keys,
-                      const int* h_splitter_ranks, int num_splitters, int my_rank, const uint64_t* h_dest_offsets,
-                      void* const* peer_keys, void* const* peer_vals, b2s_stream_t stream) {
+                      int descending, int begin_bit, int end_bit, const void* d_splitter_keys,
+                      const int* d_splitter_ranks, int num_splitters, int my_rank, const uint64_t* d_dest_offsets,
+                      void* const* peer_keys, void* const* peer_vals, uint64_t peer_capacity, b2s_stream_t stream) {
   if (!temp_storage_bytes) return (int)cudaErrorInvalidValue;
   b2s::SplitArgs a;
-  if (!b2s::fill_split_args(a, num_items, key_type, value_bytes, descending != 0, begin_bit, end_bit, h_splitter_keys,
-                            h_splitter_ranks, num_splitters, my_rank))
+  if (!b2s::fill_split_args(a, num_items, key_type, value_bytes, descending != 0, begin_bit, end_bit, d_splitter_keys,
+                            d_splitter_ranks, num_splitters, my_rank))
     return (int)cudaErrorInvalidValue;
   const b2s::KernelSet* ks = b2s::kernels_for(b2s::kKeyInfo[key_type].bytes);
   const int tile = ks->split_tile(value_bytes);
@@ -375,13 +372,13 @@ int b2s_split_scatter(void* d_temp_storage, size_t* temp_storage_bytes, const vo
     *temp_storage_bytes = L.total;
     return (int)cudaSuccess;
   }
-  if (*temp_storage_bytes < L.total || !h_dest_offsets) return (int)cudaErrorInvalidValue;
+  if (*temp_storage_bytes < L.total || !d_dest_offsets) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* base = reinterpret_cast<unsigned char*>(b2s::align_up(reinterpret_cast<uintptr_t>(d_temp_storage), 256));
   cudaError_t e = cudaMemsetAsync(base, 0, L.zero_bytes, s);
   if (e != cudaSuccess) return (int)e;
-  e = cudaMemcpyAsync(base + L.off_bins, h_dest_offsets, sizeof(uint64_t) * (size_t)(num_splitters + 1),
-                      cudaMemcpyHostToDevice, s);
+  e = cudaMemcpyAsync(base + L.off_bins, d_dest_offsets, sizeof(uint64_t) * (size_t)(num_splitters + 1),
+                      cudaMemcpyDeviceToDevice, s);
   if (e != cudaSuccess) return (int)e;
   a.pass.keys_in = d_keys_in;
   a.pass.keys_out = d_keys_out;
@@ -392,6 +389,7 @@ int b2s_split_scatter(void* d_temp_storage, size_t* temp_storage_bytes, const vo
   a.pass.bins = base + L.off_bins;
   a.pass.tile_counter = reinterpret_cast<unsigned int*>(base + L.off_ctr);
   a.peer = peer_keys != nullptr;
+  a.peer_capacity = peer_capacity;
   if (a.peer) {
     for (int d = 0; d <= num_splitters; ++d) {
       a.peer_keys[d] = peer_keys[d];

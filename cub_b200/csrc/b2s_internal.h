@@ -49,12 +49,14 @@ constexpr int kMaxSplitters = 7;
 struct SplitArgs {
   PassArgs pass;                     // .bit = begin_bit, .nbits unused; .bins = uint64 offsets per destination
   int end_bit;
-  uint64_t splitters[kMaxSplitters]; // raw keys
-  uint32_t tie;                      // bit j: splitter j was sampled on a rank <= this rank
+  const void* d_splitter_keys;       // DEVICE: raw keys, ascending in sort order
+  const int* d_splitter_ranks;       // DEVICE: source rank of every splitter
+  int my_rank;
   int num_splitters;
   void* peer_keys[8];                // non-null => write destination d into peer_keys[d] / peer_vals[d]
   void* peer_vals[8];
   bool peer;
+  uint64_t peer_capacity;            // items per peer receive buffer
   uint64_t* counts;                  // count launch: uint64[num_splitters + 1], zeroed by the caller
 };
 

@@ -115,6 +115,7 @@ void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
   p.pad_key = a.dc.pad_key;
   p.op = op;
   for (int i = 0; i < MAX_PEERS; ++i) p.peer_keys[i] = p.peer_vals[i] = nullptr;
+  p.peer_capacity = ~0ull;
 }
 
 template <int V, bool F, typename OffT, int VI>
@@ -194,9 +195,11 @@ SplitterOp<K, F> make_splitter_op(const SplitArgs& a) {
   const int nb = a.end_bit - a.pass.bit;
   op.range_mask = nb >= K * 8 ? ~W(0) : (W)((W(1) << nb) - 1);
   op.count = a.num_splitters;
-  op.tie = a.tie;
-  for (int j = 0; j < SplitterOp<K, F>::MAX_SPLITTERS; ++j)
-    op.s[j] = j < a.num_splitters ? op.sort_key((W)a.splitters[j]) : ~W(0);
+  op.d_keys = a.d_splitter_keys;
+  op.d_ranks = a.d_splitter_ranks;
+  op.my_rank = a.my_rank;
+  op.tie = 0;
+  for (int j = 0; j < SplitterOp<K, F>::MAX_SPLITTERS; ++j) op.s[j] = ~W(0);
   return op;
 }
 
@@ -214,6 +217,7 @@ cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
     p.peer_keys[i] = a.peer_keys[i];
     p.peer_vals[i] = a.peer_vals[i];
   }
+  p.peer_capacity = a.peer_capacity;
   const unsigned long long tiles = (a.pass.n + L::TILE - 1) / L::TILE;
   kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
   return cudaGetLastError();

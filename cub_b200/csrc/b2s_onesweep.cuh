@@ -49,6 +49,8 @@ struct OnesweepParams {
   // peer_keys[d] / peer_vals[d] -- receive buffers of rank d mapped into this process -- instead of keys_out.
   void* peer_keys[MAX_PEERS];
   void* peer_vals[MAX_PEERS];
+  unsigned long long peer_capacity;  // items per receive buffer: stores at or beyond it are dropped (the host detects
+                                     // the overflow from the count matrix afterwards; nothing is ever corrupted)
 };
 
 template <int KBYTES, int VBYTES, int NT, int IPT>
@@ -160,7 +162,8 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
 #pragma unroll
     for (int u = 0; u < IPT; ++u) key[u] = (W)sk[warp_base + u * 32 + lane];
   }
-  const auto op = P.op;
+  auto op = P.op;
+  op.prepare();  // no-op for DigitOp; loads the device-resident splitters for SplitterOp
   unsigned int* myhist = whist + warp * RADIX;
   const unsigned int myhist_s = smem_u32(myhist);
   const unsigned int lt = lanemask_lt();
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       const unsigned int d = op((W)k);
       const OffT dst = s_goff[d] + (OffT)pos;
       if (PEER) {
+        if ((unsigned long long)dst >= P.peer_capacity) return;
         okeys = reinterpret_cast<KeyU*>(P.peer_keys[d & (MAX_PEERS - 1)]);
         ovals = reinterpret_cast<ValU*>(P.peer_vals[d & (MAX_PEERS - 1)]);
       }

@@ -8,8 +8,10 @@
 namespace b2s {
 
 template <int KBYTES, typename OpT>
-__global__ void __launch_bounds__(1024) split_count_kernel(const void* keys_v, unsigned long long n, const OpT op,
+__global__ void __launch_bounds__(1024) split_count_kernel(const void* keys_v, unsigned long long n, const OpT op_in,
                                                            unsigned long long* counts) {
+  OpT op = op_in;
+  op.prepare();
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
   constexpr int ND = OpT::MAX_SPLITTERS + 1;

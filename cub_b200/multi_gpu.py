@@ -131,27 +131,27 @@ class LocalOps:
         self.launches += self.lib.b2s_last_launch_count()
         return dk.Current(), (dv.Current() if dv is not None else None)
 
-    def _splitter_args(self, sp_keys: np.ndarray, sp_ranks: np.ndarray):
-        sp_keys = np.ascontiguousarray(sp_keys)
-        sp_ranks = np.ascontiguousarray(sp_ranks, dtype=np.int32)
-        return (sp_keys, sp_ranks, sp_keys.ctypes.data_as(ctypes.c_void_p),
-                sp_ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(sp_keys.shape[0]))
+    @staticmethod
+    def _dptr(t: Optional[torch.Tensor]):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() else None
 
-    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank, to_host=True):
-        _k, _r, pk, pr, ns = self._splitter_args(sp_keys, sp_ranks)
+    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank) -> torch.Tensor:
+        """sp_keys (key container dtype) / sp_ranks (int32): DEVICE tensors.  Returns the int64 device tensor of counts."""
+        ns = int(sp_keys.numel())
         counts = torch.zeros(ns + 1, dtype=torch.int64, device=self.device)
         err = self.lib.b2s_split_count(ctypes.c_void_p(keys.data_ptr()), n, key_type, int(descending), begin_bit, end_bit,
-                                       pk, pr, ns, rank, ctypes.c_void_p(counts.data_ptr()), self._stream())
+                                       self._dptr(sp_keys), self._dptr(sp_ranks), ns, rank,
+                                       ctypes.c_void_p(counts.data_ptr()), self._stream())
         if err:
             raise RuntimeError(f"b2s_split_count failed: cudaError {err}")
         self.launches += 2
-        return counts.cpu().numpy() if to_host else counts
+        return counts
 
     def split_scatter(self, keys, vals, out_keys, out_vals, n, key_type, descending, begin_bit, end_bit, sp_keys,
-                      sp_ranks, rank, dest_offsets: np.ndarray, peer_keys: Optional[Sequence[int]],
-                      peer_vals: Optional[Sequence[int]], temp_holder: dict):
-        _k, _r, pk, pr, ns = self._splitter_args(sp_keys, sp_ranks)
-        offs = np.ascontiguousarray(dest_offsets, dtype=np.uint64)
+                      sp_ranks, rank, dest_offsets: torch.Tensor, peer_keys: Optional[Sequence[int]],
+                      peer_vals: Optional[Sequence[int]], temp_holder: dict, peer_capacity: int = (1 << 64) - 1):
+        """dest_offsets: int64 DEVICE tensor (items), one entry per destination."""
+        ns = int(sp_keys.numel())
         vb = vals.element_size() if vals is not None else 0
         nb = ctypes.c_size_t(0)
         pkeys = pvals = None
@@ -162,8 +162,8 @@ class LocalOps:
         common = (ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(out_keys.data_ptr()) if out_keys is not None else None,
                   ctypes.c_void_p(vals.data_ptr()) if vals is not None else None,
                   ctypes.c_void_p(out_vals.data_ptr()) if out_vals is not None else None,
-                  n, key_type, vb, int(descending), begin_bit, end_bit, pk, pr, ns, rank,
-                  offs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), pkeys, pvals)
+                  n, key_type, vb, int(descending), begin_bit, end_bit, self._dptr(sp_keys), self._dptr(sp_ranks), ns, rank,
+                  ctypes.c_void_p(dest_offsets.data_ptr()), pkeys, pvals, peer_capacity)
         err = self.lib.b2s_split_scatter(None, ctypes.byref(nb), *common, None)
         if err:
             raise RuntimeError(f"b2s_split_scatter size query failed: cudaError {err}")
@@ -242,7 +242,7 @@ class DistributedSorter:
         self.device = self.ops.device
         self.n_local = n_local
         self.samples_per_rank = samples_per_rank
-        self.capacity = int(n_local * slack) + 1024
+        self.capacity = int(n_local * slack) + 1024  # the same on every rank (n_local is the common maximum shard size)
         self.temp: dict = {}
         self._sizes_for, self._all_n = None, None
         self._fence = self.ops.empty(1, torch.int32).zero_()
@@ -346,22 +346,15 @@ class DistributedSorter:
         sk, sr = ops.sort_db([gathered, torch.empty_like(gathered)], [src, torch.empty_like(src)], G * s, kt, desc, bb, eb,
                              self.temp)
         idx = torch.arange(1, G, device=self.device, dtype=torch.int64) * s
-        # one device->host copy for both splitter keys and their source ranks
-        packed = torch.cat([sk[idx].view(torch.uint8), sr[idx].view(torch.uint8)]).cpu().numpy()
-        sp_keys = packed[: (G - 1) * self.kbytes].view(_NP_BITS[self.kbytes]).copy()
-        sp_ranks = packed[(G - 1) * self.kbytes:].view(np.int32).copy()
+        sp_keys, sp_ranks = sk[idx].contiguous(), sr[idx].contiguous()  # stay on the device: nobody waits for them
         t1 = time.perf_counter()
 
-        # 2. counts -> exchange plan
-        cm = ops.split_count(kin, n, kt, desc, bb, eb, sp_keys, sp_ranks, me, to_host=False)
+        # 2. counts -> exchange plan.  Offsets are computed on the device, so the partition kernel is enqueued before the
+        #    host looks at the count matrix (which it needs only for the size of the final local sort).
+        cm = ops.split_count(kin, n, kt, desc, bb, eb, sp_keys, sp_ranks, me)
         rows = ops.empty(G * G, torch.int64)
         dist.all_gather_into_tensor(rows, cm, group=self.group)
-        matrix = rows.cpu().numpy().reshape(G, G)
-        send_counts, send_offsets, recv_counts, total, peer_offsets = exchange_plan(matrix, me)
-        out_counts = [int(matrix[:, d].sum()) for d in range(G)]
-        if max(out_counts) > self.capacity:
-            raise RuntimeError(f"receive capacity {self.capacity} too small for {max(out_counts)} items; raise `slack`")
-        t2 = time.perf_counter()
+        dmatrix = rows.view(G, G)
 
         # 3. partition + exchange
         if self.exchange == "peer":
@@ -369,18 +362,28 @@ class DistributedSorter:
             # only once every peer's stream has reached them, i.e. has finished reading its receive buffer (the local
             # sort of the previous call).  AFTER them a tiny stream-ordered all_reduce is the fence: it completes on this
             # rank only when every rank's partition kernel -- all stores into this rank's buffer -- has completed.
-            ops.split_scatter(kin, vin, None, None, n, kt, desc, bb, eb, sp_keys, sp_ranks, me, peer_offsets,
-                              self.peer_k, self.peer_v if vin is not None else None, self.temp)
+            peer_offsets_dev = dmatrix[:me].sum(dim=0) if me > 0 else torch.zeros(G, dtype=torch.int64, device=self.device)
+            ops.split_scatter(kin, vin, None, None, n, kt, desc, bb, eb, sp_keys, sp_ranks, me, peer_offsets_dev,
+                              self.peer_k, self.peer_v if vin is not None else None, self.temp, self.capacity)
             dist.all_reduce(self._fence, group=self.group)
+            matrix = dmatrix.cpu().numpy()  # the host catches up while the partition kernel runs
+            send_counts, send_offsets, recv_counts, total, _peer_offsets = exchange_plan(matrix, me)
         else:
+            matrix = dmatrix.cpu().numpy()
+            send_counts, send_offsets, recv_counts, total, _peer_offsets = exchange_plan(matrix, me)
+            send_offsets_dev = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
             ops.split_scatter(kin, vin, self.part_k, self.part_v, n, kt, desc, bb, eb, sp_keys, sp_ranks, me,
-                              send_offsets, None, None, self.temp)
+                              send_offsets_dev, None, None, self.temp)
             dist.all_to_all_single(self.recv_k[0][:total], self.part_k[:n], [int(c) for c in recv_counts],
                                    [int(c) for c in send_counts], group=self.group)
             if vin is not None:
                 dist.all_to_all_single(self._container(self.recv_v[0])[:total], self._container(self.part_v)[:n],
                                        [int(c) for c in recv_counts], [int(c) for c in send_counts], group=self.group)
-        t3 = time.perf_counter()
+        out_counts = [int(matrix[:, d].sum()) for d in range(G)]
+        if max(out_counts) > self.capacity:
+            raise RuntimeError(f"receive capacity {self.capacity} too small for {max(out_counts)} items; raise `slack` "
+                               "(items beyond the capacity were dropped by the partition kernel, nothing was overrun)")
+        t2 = t3 = time.perf_counter()
 
         # 4. final local stable sort over the G received runs
         if total > 0:

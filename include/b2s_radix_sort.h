@@ -122,16 +122,20 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int *threa
  * The global order is (key, source rank, index on the source rank), i.e. the stable sort of the rank-order
  * concatenation of the shards.  Keys: 4- or 8-byte types; values: 0, 4 or 8 bytes.
  *
- * Splitters are (raw key, source rank) pairs in HOST memory, ascending in sort order; at most 7 (8 ranks).
+ * Splitters are (raw key, source rank) pairs in DEVICE memory (they come out of a device-side sort of the samples, and
+ * the host never has to wait for them), ascending in sort order; at most 7 (8 ranks).  The per-destination offsets
+ * of b2s_split_scatter are in device memory as well: the whole exchange is enqueued without a host round trip.
  * A local key goes to destination d = number of splitters (k*, r*) with (k*, r*) <= (key, my_rank), comparing
  * keys on bits [begin_bit, end_bit) of their bit-ordered transform.
  *
  * b2s_split_count:   d_counts[d] (uint64, num_splitters + 1 entries) = local keys destined for rank d.
  * b2s_split_scatter: stable partition of the local shard by destination.  Destination d's items are written
- *                    to  peer_keys[d] + h_dest_offsets[d]  (items) when peer_keys != NULL -- receive buffers
+ *                    to  peer_keys[d] + d_dest_offsets[d]  (items) when peer_keys != NULL -- receive buffers
  *                    of the other ranks mapped into this process, so the all-to-all exchange is fused into the
- *                    partition pass as NVLink stores -- and to  d_keys_out + h_dest_offsets[d]  otherwise
- *                    (then exchanged by an NCCL all-to-all).  Two-phase temp-storage query like the sort.
+ *                    partition pass as NVLink stores -- and to  d_keys_out + d_dest_offsets[d]  otherwise
+ *                    (then exchanged by an NCCL all-to-all).  Peer stores at item positions >= peer_capacity are
+ *                    dropped, so an under-sized receive buffer is never overrun (the caller sees the overflow in
+ *                    the count matrix).  Two-phase temp-storage query like the sort.
  */
 /* Let kernels of the CURRENT device store into memory of `peer_device` (needed once per peer before
  * b2s_split_scatter with peer buffers; idempotent). */
@@ -141,14 +145,14 @@ int b2s_enable_peer_access(int peer_device);
 int b2s_ipc_open(const void *handle64, void **d_ptr);
 int b2s_ipc_close(void *d_ptr);
 int b2s_split_count(const void *d_keys_in, uint64_t num_items, int key_type, int descending,
-                    int begin_bit, int end_bit, const void *h_splitter_keys, const int *h_splitter_ranks,
+                    int begin_bit, int end_bit, const void *d_splitter_keys, const int *d_splitter_ranks,
                     int num_splitters, int my_rank, uint64_t *d_counts, b2s_stream_t stream);
 int b2s_split_scatter(void *d_temp_storage, size_t *temp_storage_bytes,
                       const void *d_keys_in, void *d_keys_out, const void *d_values_in, void *d_values_out,
                       uint64_t num_items, int key_type, int value_bytes, int descending, int begin_bit, int end_bit,
-                      const void *h_splitter_keys, const int *h_splitter_ranks, int num_splitters, int my_rank,
-                      const uint64_t *h_dest_offsets, void *const *peer_keys, void *const *peer_vals,
-                      b2s_stream_t stream);
+                      const void *d_splitter_keys, const int *d_splitter_ranks, int num_splitters, int my_rank,
+                      const uint64_t *d_dest_offsets, void *const *peer_keys, void *const *peer_vals,
+                      uint64_t peer_capacity, b2s_stream_t stream);
 
 /*
  * Device helpers for the test/bench harness.  All enqueue on `stream`, no sync.

@@ -46,6 +46,8 @@ class CpuOps:
         return kbufs[1], (vbufs[1] if vbufs is not None else None)
 
     def _dest(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank):
+        sp_keys = _bits(sp_keys) if isinstance(sp_keys, torch.Tensor) else sp_keys
+        sp_ranks = sp_ranks.numpy() if isinstance(sp_ranks, torch.Tensor) else sp_ranks
         sk = [mg.sort_key(int(k), key_type, descending, begin_bit, end_bit) for k in sp_keys]
         dest = np.zeros(n, dtype=np.int64)
         raw = _bits(keys)[:n]
@@ -54,17 +56,16 @@ class CpuOps:
             dest[i] = sum(1 for j in range(len(sk)) if o > sk[j] or (o == sk[j] and int(sp_ranks[j]) <= rank))
         return dest
 
-    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank, to_host=True):
+    def split_count(self, keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank):
         dest = self._dest(keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank)
-        c = np.bincount(dest, minlength=len(sp_keys) + 1)
-        return c.astype(np.uint64) if to_host else torch.from_numpy(c.astype(np.int64))
+        return torch.from_numpy(np.bincount(dest, minlength=len(sp_keys) + 1).astype(np.int64))
 
     def split_scatter(self, keys, vals, out_keys, out_vals, n, key_type, descending, begin_bit, end_bit, sp_keys,
-                      sp_ranks, rank, dest_offsets, peer_keys, peer_vals, temp_holder):
+                      sp_ranks, rank, dest_offsets, peer_keys, peer_vals, temp_holder, peer_capacity=None):
         assert peer_keys is None, "the CPU stand-in only does the bucketed (all_to_all) exchange"
         dest = self._dest(keys, n, key_type, descending, begin_bit, end_bit, sp_keys, sp_ranks, rank)
         order = np.argsort(dest, kind="stable")
-        pos = np.asarray(dest_offsets, dtype=np.int64)
+        pos = dest_offsets.numpy().astype(np.int64) if isinstance(dest_offsets, torch.Tensor) else np.asarray(dest_offsets, dtype=np.int64)
         counts = np.bincount(dest, minlength=len(sp_keys) + 1)
         idx = 0
         for d in range(len(counts)):

@@ -47,13 +47,23 @@ def test_split_kernels_vs_numpy(b2s, kt, vb):
         rank = 3
         vals = np.arange(n, dtype=H.NP_BITS[vb]) if vb else None
         dk, dv = H.to_dev(raw), (H.to_dev(vals) if vb else None)
-        counts = ops.split_count(dk, n, kt, desc, bb, eb, sp_keys, sp_ranks, rank)
+        d_sp_keys = H.to_dev(sp_keys) if nsp else torch.empty(0, dtype=H.CONTAINER[kb], device="cuda")
+        d_sp_ranks = torch.from_numpy(sp_ranks).cuda()
+        counts = ops.split_count(dk, n, kt, desc, bb, eb, d_sp_keys, d_sp_ranks, rank).cpu().numpy()
         dest = _dest_np(raw, kt, desc, bb, eb, sp_keys, sp_ranks, rank)
         exp_counts = np.bincount(dest, minlength=nsp + 1)
         assert counts.tolist() == exp_counts.tolist()
-        offs = np.concatenate(([0], np.cumsum(exp_counts)[:-1])).astype(np.uint64)
+        offs = torch.from_numpy(np.concatenate(([0], np.cumsum(exp_counts)[:-1])).astype(np.int64)).cuda()
         ok, ov = torch.empty_like(dk), (torch.empty_like(dv) if vb else None)
-        ops.split_scatter(dk, dv, ok, ov, n, kt, desc, bb, eb, sp_keys, sp_ranks, rank, offs, None, None, {})
+        ops.split_scatter(dk, dv, ok, ov, n, kt, desc, bb, eb, d_sp_keys, d_sp_ranks, rank, offs, None, None, {})
+        # PEER write-out path with every "peer" pointing at the local buffer, and the capacity guard
+        ok2, ov2 = torch.zeros_like(dk), (torch.zeros_like(dv) if vb else None)
+        ops.split_scatter(dk, dv, None, None, n, kt, desc, bb, eb, d_sp_keys, d_sp_ranks, rank, offs, [ok2.data_ptr()] * 8,
+                          [ov2.data_ptr() if vb else 0] * 8, {}, peer_capacity=n - 1000)
+        torch.cuda.synchronize()
+        assert torch.equal(ok2[: n - 1000], ok[: n - 1000]) and bool((ok2[n - 1000:] == 0).all())
+        if vb:
+            assert torch.equal(ov2[: n - 1000], ov[: n - 1000]) and bool((ov2[n - 1000:] == 0).all())
         torch.cuda.synchronize()
         order = np.argsort(dest, kind="stable")
         assert np.array_equal(H.to_np(ok, raw.dtype), raw[order]), "partition is not the stable one"
