@@ -39,33 +39,36 @@ template <int BYTES> struct WideOf { using type = uint32_t; };
 template <> struct WideOf<8> { using type = unsigned long long; };
 
 // ---------------------------------------------------------------------------------------
-// Digit functor.  digit(k) = ((collapse(k) ^ flip(k)) >> bit) & mask
-//   integer keys : flip = xor_mask                       (sign bit for signed, all ones more for descending)
-//   floating keys: flip = xor_mask ^ (k<0 ? ~HIGH : 0)   with xor_mask = HIGH (asc) or ~HIGH... folded below
-//   collapse     : k == zero_from ? zero_to : k          (floating only; raw -0.0 -> +0.0 ascending,
-//                                                          raw +0.0 -> -0.0 descending == the reference's
-//                                                          post-twiddle rule expressed on raw bits)
+// Digit functor.  digit(k) = (ordered(k) >> bit) & mask
+//   integer keys : ordered(k) = k ^ xor_mask            (sign bit for signed, all ones more for descending)
+//   floating keys: t = k ^ (sign(k) ? ~0 : HIGH) ^ xor_mask   (Traits<fp>::TwiddleIn; xor_mask = ONES if descending)
+//                  ordered(k) = (t == zero_img) ? HIGH : t
+//     -0.0 and +0.0 must share their digits (never their stored bits).  Ascending, t(+0.0) = HIGH and t(-0.0) = ~HIGH;
+//     descending it is the other way round; the reference collapses -0.0 onto +0.0 ascending and +0.0 onto -0.0
+//     descending (radix_rank_sort_operations.cuh:55-66, 79-89), i.e. in BOTH directions the image ~HIGH is replaced by
+//     HIGH.  zero_img is that image as this functor computes it (for 16-bit keys held in 32-bit registers the bits
+//     above the key are ones for negative keys; they never reach a digit).
 // ---------------------------------------------------------------------------------------
 template <int KBYTES, bool IS_FLOAT>
 struct DigitOp {
   using W = typename WideOf<KBYTES>::type;
   W xor_mask;    // integer: HIGH (signed) ^ ONES (descending); float: ONES if descending else 0
-  W zero_from;   // float only
-  W zero_to;     // float only
+  W zero_img;    // float only: see above
   uint32_t bit;  // first bit of this pass' digit
   uint32_t mask; // (1 << digit_bits) - 1
 
   static constexpr int KBITS = KBYTES * 8;
+  static constexpr int WBITS = sizeof(W) * 8;
   static constexpr W ONES = KBYTES == 8 ? ~W(0) : (W)((1ull << (KBITS % 64)) - 1);
   static constexpr W HIGH = W(1) << (KBITS - 1);
 
   __device__ __forceinline__ void prepare() {}
   __host__ __device__ __forceinline__ W ordered(W k) const {
     if (IS_FLOAT) {
-      k = (k == zero_from) ? zero_to : k;
-      // Traits<fp>::TwiddleIn: negative -> flip all bits, non-negative -> flip the sign bit.
-      W neg = (k & HIGH) ? ONES : HIGH;
-      return k ^ neg ^ xor_mask;
+      // sign of the KBITS-wide key replicated over the register: 0 or ~0
+      const W m = KBYTES == 8 ? (W)((long long)k >> 63) : (W)((int)((unsigned int)k << (WBITS - KBITS)) >> 31);
+      const W t = k ^ (m | HIGH) ^ xor_mask;
+      return t == zero_img ? HIGH : t;
     } else {
       return k ^ xor_mask;
     }

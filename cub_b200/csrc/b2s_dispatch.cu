@@ -53,8 +53,10 @@ DigitConsts make_consts(const KeyInfo& ki, bool descending) {
   dc.is_float = ki.category == 2;
   if (dc.is_float) {
     dc.xor_mask = descending ? ones : 0;
-    dc.zero_from = descending ? 0 : high;
-    dc.zero_to = descending ? high : 0;
+    // image of -0.0 (ascending) / +0.0 (descending) under DigitOp::ordered before the collapse; keys narrower than
+    // the 32-bit register carry ones above the key when negative
+    const uint64_t reg_ones = bits == 64 ? ~0ull : 0xffffffffull;
+    dc.zero_img = descending ? (ones ^ high) : ((reg_ones ^ high) & (bits == 64 ? ~0ull : 0xffffffffull));
     dc.pad_key = descending ? ones : (ones ^ high);  // -NaN(all ones) / +NaN(0x7f..f) order last
   } else {
     dc.xor_mask = (ki.category == 1 ? high : 0) ^ (descending ? ones : 0);
@@ -73,9 +75,9 @@ int tuning_variant() { return g_variant; }
 struct KernelSet {
   cudaError_t (*hist)(const HistArgs&, cudaStream_t);
   cudaError_t (*onesweep)(int, const PassArgs&, cudaStream_t);
-  int (*tile)(int, int);
+  int (*tile)(int, int, bool);
   int (*num_variants)();
-  Variant (*variant)(int, int);
+  Variant (*variant)(int, int, bool);
   cudaError_t (*split_count)(const SplitArgs&, cudaStream_t);
   cudaError_t (*split)(const SplitArgs&, cudaStream_t);
   int (*split_tile)(int);
@@ -169,7 +171,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   const KernelSet* ks = kernels_for(kbytes);
   int variant = tuning_variant();
   if (variant < 0 || variant >= ks->num_variants()) variant = 0;
-  const int tile = ks->tile(variant, vbytes);
+  const int tile = ks->tile(variant, vbytes, ki.category == 2);
   const int passes = (num_bits + 7) / 8;
   const bool off64 = n >= (1ull << 30);
   const bool need_alt = !overwrite && passes > 1;
@@ -466,7 +468,7 @@ int b2s_set_variant(int variant) {
 int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, int* ipt, int* minb, int* match) {
   const b2s::KernelSet* ks = b2s::kernels_for(key_bytes);
   if (!ks || variant < 0 || variant >= ks->num_variants()) return -1;
-  const b2s::Variant v = ks->variant(variant, value_bytes);
+  const b2s::Variant v = ks->variant(variant, value_bytes, false);
   if (nt) *nt = v.nt;
   if (ipt) *ipt = v.ipt;
   if (minb) *minb = v.minb;

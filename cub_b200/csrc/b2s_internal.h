@@ -10,8 +10,7 @@ namespace b2s {
 // Runtime constants of one sort call that parameterise the digit functor (see b2s_common.cuh).
 struct DigitConsts {
   uint64_t xor_mask;
-  uint64_t zero_from;
-  uint64_t zero_to;
+  uint64_t zero_img;  // floating keys: image of the zero that is collapsed onto the other one (see DigitOp)
   uint64_t pad_key;  // raw key that orders last (bit-ordered form all ones)
   bool is_float;
 };
@@ -71,9 +70,9 @@ struct Variant {
 #define B2S_DECL_K(K)                                                                         \
   cudaError_t hist_launch_k##K(const HistArgs& a, cudaStream_t s);                            \
   cudaError_t onesweep_launch_k##K(int variant, const PassArgs& a, cudaStream_t s);           \
-  int onesweep_tile_k##K(int variant, int vbytes);                                            \
+  int onesweep_tile_k##K(int variant, int vbytes, bool is_float);                             \
   int onesweep_num_variants_k##K();                                                           \
-  Variant onesweep_variant_k##K(int variant, int vbytes);                                     \
+  Variant onesweep_variant_k##K(int variant, int vbytes, bool is_float);                      \
   cudaError_t split_count_launch_k##K(const SplitArgs& a, cudaStream_t s);                    \
   cudaError_t split_launch_k##K(const SplitArgs& a, cudaStream_t s);                          \
   int split_tile_k##K(int vbytes);

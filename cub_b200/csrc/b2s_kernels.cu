@@ -39,12 +39,13 @@ constexpr int scale_ipt(int ipt) {
   return r < 4 ? 4 : r;
 }
 
-template <int V>
+template <int V, bool F = false>
 constexpr Variant variant_cfg(int vi) {
   // {threads, items/thread, min CTAs/SM, look-back window}.  Production point from the B200 sweeps in
   // profiles/r1_tune_sweep_*.jsonl: big tiles win (longer digit runs on the scatter side, shorter look-back
   // walks), two 512-thread CTAs per SM.
-  const Variant d = Variant{512, scale_ipt<V>(20), 2, 4};
+  // floating keys need a few more registers for the sign-dependent transform: 18 items keep them spill-free
+  const Variant d = Variant{512, scale_ipt<V>(F ? 18 : 20), 2, 4};
 #ifdef B2S_TUNING
   switch (vi) {
     case 0: return d;
@@ -79,8 +80,7 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   using W = typename WideOf<K>::type;
   DigitOp<K, F> op;
   op.xor_mask = (W)dc.xor_mask;
-  op.zero_from = (W)dc.zero_from;
-  op.zero_to = (W)dc.zero_to;
+  op.zero_img = (W)dc.zero_img;
   op.bit = (uint32_t)bit;
   op.mask = nbits >= 32 ? 0xffffffffu : (1u << nbits) - 1u;
   return op;
@@ -120,7 +120,7 @@ void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
 
 template <int V, bool F, typename OffT, int VI>
 cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
-  constexpr Variant c = variant_cfg<V>(VI);
+  constexpr Variant c = variant_cfg<V, F>(VI);
   constexpr int TILE = c.nt * c.ipt;
   using L = OnesweepSmem<K, V, c.nt, c.ipt>;
   OnesweepParams<K, DigitOp<K, F>> p;
@@ -269,20 +269,22 @@ cudaError_t CAT(onesweep_launch_k, B2S_K)(int variant, const PassArgs& a, cudaSt
   }
 }
 
-Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes) {
+Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes, bool is_float) {
+#define B2S_VCASE(V) case V: return is_float ? variant_cfg<V, true>(variant) : variant_cfg<V, false>(variant);
   switch (vbytes) {
-    case 0: return variant_cfg<0>(variant);
-    case 1: return variant_cfg<1>(variant);
-    case 2: return variant_cfg<2>(variant);
-    case 4: return variant_cfg<4>(variant);
-    case 8: return variant_cfg<8>(variant);
-    case 16: return variant_cfg<16>(variant);
+    B2S_VCASE(0)
+    B2S_VCASE(1)
+    B2S_VCASE(2)
+    B2S_VCASE(4)
+    B2S_VCASE(8)
+    B2S_VCASE(16)
     default: return Variant{0, 0, 0, 0, 0};
   }
+#undef B2S_VCASE
 }
 
-int CAT(onesweep_tile_k, B2S_K)(int variant, int vbytes) {
-  const Variant v = CAT(onesweep_variant_k, B2S_K)(variant, vbytes);
+int CAT(onesweep_tile_k, B2S_K)(int variant, int vbytes, bool is_float) {
+  const Variant v = CAT(onesweep_variant_k, B2S_K)(variant, vbytes, is_float);
   return v.nt * v.ipt;
 }
 
