@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--cases", default="k4v4,k4v0,k8v4")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune.jsonl"))
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--ablate", action="store_true", help="also time the wrong-by-design ablation variants (k4 only)")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     b2s = _lib.load()
@@ -96,6 +97,8 @@ def main():
             nt, ipt, minb, match = (ctypes.c_int() for _ in range(4))
             b2s.b2s_describe_variant(kbytes, vbytes, v, ctypes.byref(nt), ctypes.byref(ipt), ctypes.byref(minb),
                                      ctypes.byref(match))
+            if (match.value >> 16) and not a.ablate:
+                continue  # timing-only ablations write garbage; never run them in a normal sweep
             b2s.b2s_set_variant(v)
             try:
                 r = time_sort(b2s.b2s_radix_sort_db, keys, vals, kt, a.iters)

@@ -54,6 +54,7 @@ struct DigitOp {
   using W = typename WideOf<KBYTES>::type;
   W xor_mask;    // integer: HIGH (signed) ^ ONES (descending); float: ONES if descending else 0
   W zero_img;    // float only: see above
+  uint32_t xor_digit;  // integer: (xor_mask >> bit) & mask, so that a digit is one shift + one 3-input logic op
   uint32_t bit;  // first bit of this pass' digit
   uint32_t mask; // (1 << digit_bits) - 1
 
@@ -73,7 +74,10 @@ struct DigitOp {
       return k ^ xor_mask;
     }
   }
-  __device__ __forceinline__ uint32_t operator()(W k) const { return (uint32_t)(ordered(k) >> bit) & mask; }
+  __device__ __forceinline__ uint32_t operator()(W k) const {
+    if (IS_FLOAT) return (uint32_t)(ordered(k) >> bit) & mask;
+    return ((uint32_t)(k >> bit) ^ xor_digit) & mask;  // == ((k ^ xor_mask) >> bit) & mask
+  }
 };
 
 // Destination functor of the multi-GPU partition pass: "digit" = number of splitters that order at or before
@@ -189,33 +193,53 @@ __device__ __forceinline__ uint32_t lanemask_le() {
   return m;
 }
 
-// Peer mask of lanes holding the same BITS-bit digit: one ballot per digit bit, 4 SASS
-// instructions per bit (LOP3->P, VOTE, @!P LOP3, LOP3).
+// Peer mask of lanes holding the same BITS-bit digit.  Per digit bit: x_i = ballot(bit_i), complemented in the lanes
+// whose bit is clear (the lanes that agree with me on bit i); the peer mask is the AND of the x_i, combined three at a
+// time with 3-input LOP3s (depth 2-3 instead of a chain of 8).  SASS per row of 32 keys: 1-2 R2P/LOP3.P for the
+// predicates, BITS x (VOTE + predicated LOP3) and BITS/2 LOP3 -- 21 instructions for 8 bits.
 template <int I>
-__device__ __forceinline__ void match_bit(uint32_t& m, uint32_t d) {
+__device__ __forceinline__ uint32_t agree_bit(uint32_t d) {
+  uint32_t b;
   asm volatile("{\n"
       ".reg .pred p;\n"
-      ".reg .b32 t, b;\n"
+      ".reg .b32 t;\n"
       "and.b32 t, %1, %2;\n"
       "setp.ne.u32 p, t, 0;\n"
-      "vote.sync.ballot.b32 b, p, 0xffffffff;\n"
-      "@!p not.b32 b, b;\n"
-      "and.b32 %0, %0, b;\n"
+      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      "@!p not.b32 %0, %0;\n"
       "}\n"
-      : "+r"(m)
+      : "=r"(b)
       : "r"(d), "n"(1u << I));
+  return b;
+}
+__device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
 }
 template <int BITS>
 __device__ __forceinline__ uint32_t match_ballot(uint32_t d) {
-  uint32_t m = 0xffffffffu;
-  match_bit<0>(m, d);
-  if (BITS > 1) match_bit<1>(m, d);
-  if (BITS > 2) match_bit<2>(m, d);
-  if (BITS > 3) match_bit<3>(m, d);
-  if (BITS > 4) match_bit<4>(m, d);
-  if (BITS > 5) match_bit<5>(m, d);
-  if (BITS > 6) match_bit<6>(m, d);
-  if (BITS > 7) match_bit<7>(m, d);
+  static_assert(BITS >= 1 && BITS <= 11, "digit width");
+  uint32_t x[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) x[i] = 0xffffffffu;
+  x[0] = agree_bit<0>(d);
+  if (BITS > 1) x[1] = agree_bit<1>(d);
+  if (BITS > 2) x[2] = agree_bit<2>(d);
+  if (BITS > 3) x[3] = agree_bit<3>(d);
+  if (BITS > 4) x[4] = agree_bit<4>(d);
+  if (BITS > 5) x[5] = agree_bit<5>(d);
+  if (BITS > 6) x[6] = agree_bit<6>(d);
+  if (BITS > 7) x[7] = agree_bit<7>(d);
+  if (BITS > 8) x[8] = agree_bit<8>(d);
+  if (BITS > 9) x[9] = agree_bit<9>(d);
+  if (BITS > 10) x[10] = agree_bit<10>(d);
+  if (BITS <= 2) return x[0] & x[1];
+  uint32_t m = and3(x[0], x[1], x[2]);
+  if (BITS > 3) m = BITS > 4 ? and3(m, x[3], x[4]) : (m & x[3]);
+  if (BITS > 5) m = BITS > 6 ? and3(m, x[5], x[6]) : (m & x[5]);
+  if (BITS > 7) m = BITS > 8 ? and3(m, x[7], x[8]) : (m & x[7]);
+  if (BITS > 9) m = BITS > 10 ? and3(m, x[9], x[10]) : (m & x[9]);
   return m;
 }
 // (The hardware MATCH.ANY instruction is not an option: on B200 its cost grows with the number of distinct
@@ -229,16 +253,28 @@ __device__ __forceinline__ uint32_t bfind(uint32_t x) {
   return r;
 }
 
-// Leader-only shared-memory fetch-add, predicated (no branch): returns the old value on the
-// leader lane, 0 elsewhere.
+// Optimisation barrier: the compiler may not assume anything about the value afterwards.  Used to make it RECOMPUTE
+// a digit from its key (2 instructions) instead of keeping one more register per item alive across block barriers.
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+__device__ __forceinline__ unsigned long long opaque(unsigned long long x) {
+  asm volatile("" : "+l"(x));
+  return x;
+}
+
+// Leader-only shared-memory fetch-add: returns the old value on the lanes where `pred` holds; the result is
+// UNSPECIFIED on the other lanes (callers only ever read the leader's copy through a shuffle), which saves
+// initialising it.
 __device__ __forceinline__ uint32_t atoms_add_if(bool pred, uint32_t smem_addr, uint32_t v) {
-  uint32_t old = 0;
+  uint32_t old;
   asm volatile("{\n"
                ".reg .pred p;\n"
                "setp.ne.u32 p, %3, 0;\n"
                "@p atom.shared.add.u32 %0, [%1], %2;\n"
                "}\n"
-               : "+r"(old)
+               : "=r"(old)
                : "r"(smem_addr), "r"(v), "r"((uint32_t)pred)
                : "memory");
   return old;

@@ -41,15 +41,17 @@ constexpr int scale_ipt(int ipt) {
 
 template <int V, bool F = false>
 constexpr Variant variant_cfg(int vi) {
-  // {threads, items/thread, min CTAs/SM, look-back window}.  Production point from the B200 sweeps in
-  // profiles/r1_tune_sweep_*.jsonl: big tiles win (longer digit runs on the scatter side, shorter look-back
-  // walks), two 512-thread CTAs per SM.
-  // floating keys need a few more registers for the sign-dependent transform: 18 items keep them spill-free
-  const Variant d = Variant{512, scale_ipt<V>(F ? 18 : 20), 2, 4};
+  // {threads, items/thread, min CTAs/SM, look-back window}.  Production points from the B200 sweeps in
+  // profiles/r1_tune_sweep_*.jsonl (last sweep: tune_r1q): three 384-thread CTAs per SM are best or within 1 % of the
+  // best for every shape except small pairs (K + V <= 8 bytes with values), where four 256-thread CTAs win by 2-4 %.
+  // Floating keys take one or two items less (their transform needs registers).
+  const bool small_pairs = V > 0 && K + V <= 8;
+  const Variant d = small_pairs ? Variant{256, scale_ipt<V>(F ? 18 : 20), 4, 4, 0}
+                                : Variant{384, scale_ipt<V>(F ? 17 : 19), 3, 4, 0};
 #ifdef B2S_TUNING
   switch (vi) {
     case 0: return d;
-    case 1: return Variant{512, scale_ipt<V>(20), 2, 1};
+    case 1: return Variant{512, scale_ipt<V>(20), 2, 4};
     case 2: return Variant{512, scale_ipt<V>(20), 2, 2};
     case 3: return Variant{512, scale_ipt<V>(20), 2, 8};
     case 4: return Variant{512, scale_ipt<V>(16), 2, 4};
@@ -83,6 +85,7 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   op.zero_img = (W)dc.zero_img;
   op.bit = (uint32_t)bit;
   op.mask = nbits >= 32 ? 0xffffffffu : (1u << nbits) - 1u;
+  op.xor_digit = (uint32_t)((W)dc.xor_mask >> bit) & op.mask;
   return op;
 }
 

@@ -189,14 +189,16 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       d_next = op(key[u + 1]);
       m_next = match_ballot<RADIX_BITS>(d_next);
     }
-    if (u > 0) rk[u - 1] = (bcast_prev + below_prev) | (d_prev << 16);
+    // opaque(): the packed word must be formed HERE; otherwise the compiler keeps rank parts and masks alive across the
+    // block barriers and re-derives the digit from the key afterwards (11 instructions per item instead of 6)
+    if (u > 0) rk[u - 1] = opaque((bcast_prev + below_prev) | (d_prev << 16));
     bcast_prev = __shfl_sync(0xffffffffu, raw, leader);
     below_prev = below;
     d_prev = d;
     d = d_next;
     m = m_next;
   }
-  if (!(ABL & 4)) rk[IPT - 1] = (bcast_prev + below_prev) | (d_prev << 16);
+  if (!(ABL & 4)) rk[IPT - 1] = opaque((bcast_prev + below_prev) | (d_prev << 16));
   __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
 
   // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases
