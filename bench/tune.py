@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--cases", default="k4v4,k4v0,k8v4")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune.jsonl"))
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--variants", default="", help="comma-separated variant ids to time (default: all)")
     ap.add_argument("--ablate", action="store_true", help="also time the wrong-by-design ablation variants (k4 only)")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -93,7 +94,10 @@ def main():
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")
         nv = b2s.b2s_describe_variant(kbytes, vbytes, 0, None, None, None, None)
+        only = [int(x) for x in a.variants.split(",") if x != ""]
         for v in range(nv):
+            if only and v not in only:
+                continue
             nt, ipt, minb, match = (ctypes.c_int() for _ in range(4))
             b2s.b2s_describe_variant(kbytes, vbytes, v, ctypes.byref(nt), ctypes.byref(ipt), ctypes.byref(minb),
                                      ctypes.byref(match))
@@ -112,7 +116,8 @@ def main():
             if golden is not None:
                 ok = bool(torch.equal(ko, golden[0]) and (vo is None or torch.equal(vo, golden[1])))
             rec = {"case": case, "n": n, "impl": "b2s", "variant": v, "nt": nt.value, "ipt": ipt.value,
-                   "minb": minb.value, "match": match.value, "best_ms": best, "median_ms": med,
+                   "minb": minb.value, "match": match.value, "mode": b2s.b2s_variant_mode(kbytes, vbytes, v) & 3,
+                   "pfd": b2s.b2s_variant_mode(kbytes, vbytes, v) >> 8, "best_ms": best, "median_ms": med,
                    "gkeys_s": n / best / 1e6, "algo_gbs": algo_bytes / best / 1e6, "bit_exact_vs_ref": ok}
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")

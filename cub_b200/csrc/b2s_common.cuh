@@ -163,6 +163,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       : "memory");
 }
 
+// L2 prefetch of a contiguous global window (16-byte aligned address and size); no shared memory, no completion.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// Orders earlier generic-proxy accesses to shared memory (LDS/STS) before later async-proxy ones (TMA writes).
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // gpu-scope relaxed loads / stores for the look-back status words (the word carries flag AND
 // value, so no acquire/release pairing is needed; L1 is bypassed by the scope).
 __device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
@@ -197,19 +206,34 @@ __device__ __forceinline__ uint32_t lanemask_le() {
 // whose bit is clear (the lanes that agree with me on bit i); the peer mask is the AND of the x_i, combined three at a
 // time with 3-input LOP3s (depth 2-3 instead of a chain of 8).  SASS per row of 32 keys: 1-2 R2P/LOP3.P for the
 // predicates, BITS x (VOTE + predicated LOP3) and BITS/2 LOP3 -- 21 instructions for 8 bits.
-template <int I>
-__device__ __forceinline__ uint32_t agree_bit(uint32_t d) {
+template <int I, bool NOT_ON_FMA>
+__device__ __forceinline__ uint32_t agree_bit(uint32_t d, uint32_t ones) {
   uint32_t b;
-  asm volatile("{\n"
-      ".reg .pred p;\n"
-      ".reg .b32 t;\n"
-      "and.b32 t, %1, %2;\n"
-      "setp.ne.u32 p, t, 0;\n"
-      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
-      "@!p not.b32 %0, %0;\n"
-      "}\n"
-      : "=r"(b)
-      : "r"(d), "n"(1u << I));
+  if (NOT_ON_FMA) {
+    // ~b == b * -1 + -1: the complement as an IMAD, i.e. on the FMA pipe, which the ranking loop leaves idle, instead of one
+    // more LOP3 on the half-rate ALU pipe that bounds it
+    asm volatile("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %1, %2;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+        "@!p mad.lo.u32 %0, %0, %3, %3;\n"
+        "}\n"
+        : "=r"(b)
+        : "r"(d), "n"(1u << I), "r"(ones));  // `ones` must not be a compile-time constant, or ptxas turns this into IADD3
+  } else {
+    asm volatile("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %1, %2;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+        "@!p not.b32 %0, %0;\n"
+        "}\n"
+        : "=r"(b)
+        : "r"(d), "n"(1u << I));
+  }
   return b;
 }
 __device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
@@ -217,23 +241,23 @@ __device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c) {
   asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
-template <int BITS>
-__device__ __forceinline__ uint32_t match_ballot(uint32_t d) {
+template <int BITS, bool NOT_ON_FMA = false>
+__device__ __forceinline__ uint32_t match_ballot(uint32_t d, uint32_t ones = 0xffffffffu) {
   static_assert(BITS >= 1 && BITS <= 11, "digit width");
   uint32_t x[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) x[i] = 0xffffffffu;
-  x[0] = agree_bit<0>(d);
-  if (BITS > 1) x[1] = agree_bit<1>(d);
-  if (BITS > 2) x[2] = agree_bit<2>(d);
-  if (BITS > 3) x[3] = agree_bit<3>(d);
-  if (BITS > 4) x[4] = agree_bit<4>(d);
-  if (BITS > 5) x[5] = agree_bit<5>(d);
-  if (BITS > 6) x[6] = agree_bit<6>(d);
-  if (BITS > 7) x[7] = agree_bit<7>(d);
-  if (BITS > 8) x[8] = agree_bit<8>(d);
-  if (BITS > 9) x[9] = agree_bit<9>(d);
-  if (BITS > 10) x[10] = agree_bit<10>(d);
+  x[0] = agree_bit<0, NOT_ON_FMA>(d, ones);
+  if (BITS > 1) x[1] = agree_bit<1, NOT_ON_FMA>(d, ones);
+  if (BITS > 2) x[2] = agree_bit<2, NOT_ON_FMA>(d, ones);
+  if (BITS > 3) x[3] = agree_bit<3, NOT_ON_FMA>(d, ones);
+  if (BITS > 4) x[4] = agree_bit<4, NOT_ON_FMA>(d, ones);
+  if (BITS > 5) x[5] = agree_bit<5, NOT_ON_FMA>(d, ones);
+  if (BITS > 6) x[6] = agree_bit<6, NOT_ON_FMA>(d, ones);
+  if (BITS > 7) x[7] = agree_bit<7, NOT_ON_FMA>(d, ones);
+  if (BITS > 8) x[8] = agree_bit<8, NOT_ON_FMA>(d, ones);
+  if (BITS > 9) x[9] = agree_bit<9, NOT_ON_FMA>(d, ones);
+  if (BITS > 10) x[10] = agree_bit<10, NOT_ON_FMA>(d, ones);
   if (BITS <= 2) return x[0] & x[1];
   uint32_t m = and3(x[0], x[1], x[2]);
   if (BITS > 3) m = BITS > 4 ? and3(m, x[3], x[4]) : (m & x[3]);

@@ -71,6 +71,9 @@ int g_variant = [] {
   return e ? std::atoi(e) : 0;
 }();
 int tuning_variant() { return g_variant; }
+// Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
+unsigned long long* g_trace = nullptr;
+int g_trace_pass = -1;
 
 struct KernelSet {
   cudaError_t (*hist)(const HistArgs&, cudaStream_t);
@@ -252,6 +255,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     a.nbits = (end_bit - a.bit) < 8 ? (end_bit - a.bit) : 8;
     a.off64 = off64;
     a.vbytes = vbytes;
+    a.trace = (g_trace_pass == p) ? g_trace : nullptr;
     e = ks->onesweep(variant, a, stream);
     if (e != cudaSuccess) return (int)e;
     g_last_launches++;
@@ -474,6 +478,18 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
   if (minb) *minb = v.minb;
   if (match) *match = (v.lbw << 8) | (v.abl << 16);  // legacy slot: look-back window in bits 8+, ablation in 16+
   return ks->num_variants();
+}
+
+int b2s_set_trace(void* d_trace, int pass) {
+  b2s::g_trace = reinterpret_cast<unsigned long long*>(d_trace);
+  b2s::g_trace_pass = d_trace ? pass : -1;
+  return 0;
+}
+
+int b2s_variant_mode(int key_bytes, int value_bytes, int variant) {
+  const b2s::KernelSet* ks = b2s::kernels_for(key_bytes);
+  if (!ks || variant < 0 || variant >= ks->num_variants()) return -1;
+  return ks->variant(variant, value_bytes, false).mode;
 }
 
 }  // extern "C"

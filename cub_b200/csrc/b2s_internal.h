@@ -41,6 +41,7 @@ struct PassArgs {
   int nbits;     // digit width of this pass (<= 8)
   bool off64;
   int vbytes;
+  unsigned long long* trace;  // tuning builds: per-tile phase timestamps (u64[tiles][16]) of one selected pass, else null
 };
 
 // Multi-GPU partition pass (b2s_split): destination = number of splitters ordering at or before the key.
@@ -64,6 +65,7 @@ struct Variant {
   int nt, ipt, minb;
   int lbw;  // look-back window (predecessor tiles read per round trip)
   int abl;  // tuning builds only: timing ablation switches (0 in every product variant)
+  int mode; // bits 0-1: 0 one tile per CTA, 1/2 persistent CTAs (late/early tile claim); bits 8+: L2 prefetch distance (tiles)
 };
 
 // Implemented once per key width in b2s_kernels.cu (-DB2S_K=1|2|4|8)

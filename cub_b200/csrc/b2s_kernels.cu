@@ -24,7 +24,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 18;
+constexpr int NUM_VARIANTS = 40;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -69,6 +69,30 @@ constexpr Variant variant_cfg(int vi) {
     case 15: return Variant{512, scale_ipt<V>(20), 2, 4, 8};
     case 16: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 2};
     case 17: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 8};
+    // L2 prefetch distance / persistent CTAs (see MODE in b2s_onesweep.cuh)
+    case 18: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 296 << 8};
+    case 19: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 592 << 8};
+    case 20: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 74 << 8};
+    case 21: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1};
+    case 22: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2};
+    case 23: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1 | 4};
+    case 24: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2 | 4};
+    case 25: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 222 << 8};
+    case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 1};
+    case 27: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 2};
+    case 28: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 148 << 8};
+    case 29: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 1};
+    case 30: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 2};
+    case 31: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 8};
+    case 32: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 8 | (148 << 8)};
+    case 33: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | (222 << 8)};
+    case 34: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 8 | (148 << 8)};
+    case 35: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2 | 8};
+    // phase-timestamp traces (bit 4)
+    case 36: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16};
+    case 37: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 1};
+    case 38: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16};
+    case 39: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 16};
     default: return d;
   }
 #else
@@ -104,6 +128,20 @@ cudaError_t ensure_smem(KernT kern, int bytes) {
   return e;
 }
 
+// CTAs of a persistent launch: SMs of the current device x CTAs per SM.
+inline int resident_ctas(int per_sm) {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
+  }
+  return sms[dev] * per_sm;
+}
+
 template <typename OpT>
 void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
   p.keys_in = a.keys_in;
@@ -116,6 +154,8 @@ void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
   p.tile_counter = a.tile_counter;
   p.n = a.n;
   p.pad_key = a.dc.pad_key;
+  p.ones = 0xffffffffu;
+  p.trace = a.trace;
   p.op = op;
   for (int i = 0; i < MAX_PEERS; ++i) p.peer_keys[i] = p.peer_vals[i] = nullptr;
   p.peer_capacity = ~0ull;
@@ -129,10 +169,12 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   OnesweepParams<K, DigitOp<K, F>> p;
   fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
   const unsigned long long tiles = (a.n + TILE - 1) / TILE;
-  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false, c.abl>;
+  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, c.lbw, false, c.abl, c.mode>;
   cudaError_t e = ensure_smem(kern, L::TOTAL);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
+  unsigned long long grid = tiles;
+  if ((c.mode & 3) && grid > (unsigned long long)resident_ctas(c.minb)) grid = resident_ctas(c.minb);
+  kern<<<(unsigned int)grid, c.nt, L::TOTAL, s>>>(p);
   return cudaGetLastError();
 }
 

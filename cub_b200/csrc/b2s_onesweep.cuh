@@ -44,6 +44,8 @@ struct OnesweepParams {
   unsigned int* tile_counter;
   unsigned long long n;
   unsigned long long pad_key;  // raw key whose bit-ordered form is all ones
+  unsigned long long* trace;   // tuning builds, MODE bit 4: u64[tiles][16] phase timestamps (null otherwise)
+  unsigned int ones;           // 0xffffffff, as a launch parameter so that the compiler cannot fold it (see agree_bit)
   OpT op;              // key -> digit of this pass (DigitOp), or key -> destination rank (SplitterOp)
   // PEER launches only (multi-GPU exchange fused into the partition pass): digit d is written to
   // peer_keys[d] / peer_vals[d] -- receive buffers of rank d mapped into this process -- instead of keys_out.
@@ -69,8 +71,22 @@ struct OnesweepSmem {
 
 // ABL: timing-only ablation switches for bench/tune.py (results are WRONG when non-zero; never used by the product):
 //   1 = no global stores in P4, 2 = no P4 at all, 4 = no ranking sweep, 8 = no look-back walk, 16 = no P3/P4 value path
-template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0>
+// MODE: bits 0-1 = 0 one tile per CTA (grid = tiles) | 1 persistent CTA (grid = resident CTAs), next tile claimed after the
+//       write-out | 2 persistent, next tile claimed before the write-out (claim latency hidden behind it);
+//       bit 2 = (experiment) cross-proxy fence before a persistent CTA re-fills its staging buffers;
+//       bit 3 = complement of the ballots on the FMA pipe (IMAD) instead of the ALU pipe (LOP3);
+//       bit 4 = (tuning) thread 0 records the SM clock at every phase boundary into P.trace;
+//       bits 8+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
+template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0,
+          int MODE = 0>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, OpT> P) {
+  constexpr int PERSIST = MODE & 3;
+  constexpr bool TRACE = (MODE & 16) != 0;
+#define B2S_TRACE(slot)                                                                  \
+  do {                                                                                   \
+    if (TRACE && P.trace && threadIdx.x == 0) P.trace[tile * 16 + (slot)] = clock64();   \
+  } while (0)
+  constexpr int PFD = MODE >> 8;
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
   using ValU = typename UIntOf<VBYTES ? VBYTES : 1>::type;
@@ -94,9 +110,8 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   unsigned int* s_wtot = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 16);  // [8]
   unsigned int* s_tile = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 64);
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
+  int tid = threadIdx.x;
+  long long t_entry = TRACE ? clock64() : 0;
 
   // ---- P0: claim a tile (launch order == input order), arm the barriers, clear counters
   if (tid == 0) {
@@ -109,7 +124,26 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
   __syncthreads();
 
+  const unsigned long long num_tiles = (P.n + TILE - 1) / TILE;
+  unsigned int phase = 0;  // parity of the mbarrier phase the next bulk copies complete
+  for (;;) {               // one iteration per tile; a single one unless PERSIST
+  // persistent CTAs: everything derived from the thread index is re-derived per tile (opaque) instead of being hoisted
+  // out of the loop, where it would cost registers for the whole tile
+  if (PERSIST) tid = (int)opaque((unsigned int)tid);
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
   const unsigned long long tile = *s_tile;
+  if (PERSIST && tile >= num_tiles) break;
+  if (TRACE && P.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    unsigned int smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    P.trace[tile * 16 + 0] = gt;
+    P.trace[tile * 16 + 15] = smid;
+  }
+  if (TRACE && P.trace && threadIdx.x == 0) P.trace[tile * 16 + 11] = (unsigned long long)t_entry;  // CTA entry / previous tile done
+  B2S_TRACE(1);  // tile claimed
   const unsigned long long tile_base = tile * TILE;
   const unsigned long long remain = P.n - tile_base;
   const bool full = remain >= (unsigned long long)TILE;
@@ -129,8 +163,21 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   bulk = bulk && (kshift == 0 || remain * KBYTES >= (unsigned long long)kbytes - kshift) &&
          (vshift == 0 || remain * VBYTES >= (unsigned long long)vbytes - vshift);
 
+  // kept as an integer: a predicate that lives across the ranking loop would collide with the seven the ballots need
+  const unsigned int bulk_flag = PERSIST ? opaque(bulk ? 1u : 0u) : 0u;
+  if (PFD && tid == 32) {
+    // ask L2 for a tile that will be claimed about one CTA lifetime from now, so that its TMA copies hit L2
+    if (tile + PFD + 1 < num_tiles) {
+      bulk_prefetch_l2(reinterpret_cast<const void*>((kaddr + (unsigned long long)PFD * TILE * KBYTES) & ~(uintptr_t)15),
+                       (unsigned int)(TILE * KBYTES) & ~15u);
+      if (HAS_VALUES)
+        bulk_prefetch_l2(reinterpret_cast<const void*>((vaddr + (unsigned long long)PFD * TILE * VBYTES) & ~(uintptr_t)15),
+                         (unsigned int)(TILE * VBYTES) & ~15u);
+    }
+  }
   if (bulk) {
     if (tid == 0) {
+      if (PERSIST && (MODE & 4)) fence_proxy_async();  // (experiment) cross-proxy fence before re-filling the buffers
       mbar_expect_tx(&bar[0], kbytes);
       bulk_g2s(stage_k, reinterpret_cast<const void*>(kaddr - kshift), kbytes, &bar[0]);
       if (HAS_VALUES) {
@@ -157,7 +204,8 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   W key[IPT];
   unsigned int rk[IPT];  // (digit << 16) | rank inside this warp's digit bucket
   {
-    if (bulk) mbar_wait(&bar[0], 0);
+    if (bulk) mbar_wait(&bar[0], phase);
+    B2S_TRACE(2);  // keys staged
     const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + kshift);
 #pragma unroll
     for (int u = 0; u < IPT; ++u) key[u] = (W)sk[warp_base + u * 32 + lane];
@@ -172,7 +220,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   //   ->  rank of row u-1 from its broadcast (issued one iteration ago)  ->  SHFL broadcast of row u's atomic.
   // Neither the ATOMS->SHFL nor the SHFL->use latency is exposed; only the shared-memory pipe's throughput is.
   unsigned int d = op(key[0]);
-  unsigned int m = match_ballot<RADIX_BITS>(d);
+  unsigned int m = match_ballot<RADIX_BITS, (MODE & 8) != 0>(d, P.ones);
   unsigned int bcast_prev = 0, below_prev = 0, d_prev = 0;
   if (ABL & 4) {
 #pragma unroll
@@ -187,7 +235,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     unsigned int d_next = 0, m_next = 0;
     if (u + 1 < IPT) {
       d_next = op(key[u + 1]);
-      m_next = match_ballot<RADIX_BITS>(d_next);
+      m_next = match_ballot<RADIX_BITS, (MODE & 8) != 0>(d_next, P.ones);
     }
     // opaque(): the packed word must be formed HERE; otherwise the compiler keeps rank parts and masks alive across the
     // block barriers and re-derives the digit from the key afterwards (11 instructions per item instead of 6)
@@ -200,6 +248,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   }
   if (!(ABL & 4)) rk[IPT - 1] = opaque((bcast_prev + below_prev) | (d_prev << 16));
   __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
+  B2S_TRACE(3);  // ranked
 
   // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases
   OffT* status = reinterpret_cast<OffT*>(P.status) + tile * RADIX;
@@ -237,6 +286,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     }
   }
   __syncthreads();  // S3: per-warp bases ready
+  B2S_TRACE(4);  // digit scan done
 
   // ---- P3: reorder keys in shared memory (staged keys were all consumed before S2)
   {
@@ -251,12 +301,13 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   // values: staged values -> registers (re-using the key registers), barrier, then in-place reorder
   ValU val[HAS_VALUES ? IPT : 1];
   if (HAS_VALUES) {
-    if (bulk) mbar_wait(&bar[1], 0);
+    if (bulk) mbar_wait(&bar[1], phase);
     const ValU* sv = reinterpret_cast<const ValU*>(stage_v + vshift);
 #pragma unroll
     for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
   }
 
+  B2S_TRACE(5);  // keys reordered, values in registers
   // ---- look-back: exclusive prefix of this tile for digit `tid`.  Each round trip reads the next LBW
   // predecessors with independent loads -- issued only now, so that they see fresh state: a predecessor
   // publishes its inclusive prefix one round trip after ITS look-back starts, so a load issued before the
@@ -289,13 +340,19 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     }
     s_goff[tid] = reinterpret_cast<const OffT*>(P.bins)[tid] + excl - (OffT)tile_excl;
   }
+  B2S_TRACE(6);  // look-back of digit 0 done
   if (HAS_VALUES) {
     __syncthreads();  // S3b: every staged value is in a register
+    B2S_TRACE(7);  // everybody's look-back done
     ValU* sv = reinterpret_cast<ValU*>(stage_v);
 #pragma unroll
     for (int u = 0; u < IPT; ++u) sv[rk[u]] = val[u];
   }
   __syncthreads();  // S4
+  B2S_TRACE(8);  // values reordered
+
+  unsigned int next_tile = 0;
+  if (PERSIST == 2 && tid == 0) next_tile = atomicAdd(P.tile_counter, 1u);
 
   // ---- P4: coalesced write-out of digit runs
   {
@@ -328,6 +385,19 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       for (int pos = tid; pos < valid; pos += NT) emit(pos);
     }
   }
+  B2S_TRACE(9);  // thread 0's stores issued
+  if (!PERSIST) break;
+  // ---- next tile of a persistent CTA: claim, clear the warp counters (unused since P3); the barrier also orders the
+  // write-out's reads of the staging buffers before the next TMA copies into them
+  if (tid == 0) *s_tile = PERSIST == 2 ? next_tile : atomicAdd(P.tile_counter, 1u);
+#pragma unroll
+  for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
+  phase ^= bulk_flag;
+  __syncthreads();
+  B2S_TRACE(10);  // everybody's stores issued, next tile claimed
+  if (TRACE) t_entry = clock64();
+  }  // tile loop
+#undef B2S_TRACE
 }
 
 }  // namespace b2s
