@@ -18,9 +18,9 @@ from tests import harness as H  # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "bench"))
 from tune import CASES, time_sort  # noqa: E402
 
-PHASES = [("claim(entry->tile known)", 11, 1), ("key TMA wait", 1, 2), ("rank", 2, 3), ("digit scan P2", 3, 4),
+PHASES = [("key TMA wait", 1, 2), ("rank", 2, 3), ("digit scan P2", 3, 4),
           ("key scatter+val load", 4, 5), ("look-back (digit 0)", 5, 6), ("barrier S3b (all look-backs)", 6, 7),
-          ("value scatter+S4", 7, 8), ("write-out issue (thread 0)", 8, 9), ("lifetime entry->stores issued", 11, 9),
+          ("value scatter+S4", 7, 8), ("write-out issue (thread 0)", 8, 9), ("lifetime tile known->stores issued", 1, 9),
           ("end barrier+claim (persistent)", 9, 10)]
 
 
@@ -68,6 +68,12 @@ def main():
             q = torch.quantile(d, torch.tensor([0.1, 0.5, 0.9], dtype=torch.double))
             rec["phases_us"][name] = {"mean": d.mean().item(), "p10": q[0].item(), "p50": q[1].item(), "p90": q[2].item()}
             print(f"  {name:38s} mean {d.mean().item():7.2f}  p10 {q[0].item():7.2f}  p50 {q[1].item():7.2f}  p90 {q[2].item():7.2f} us")
+        for name, slot in (("look-back round trips", 12), ("look-back spin reloads", 13), ("predecessors summed", 14)):
+            d = t[1:, slot]
+            q = torch.quantile(d, torch.tensor([0.1, 0.5, 0.9], dtype=torch.double))
+            print(f"  {name:38s} mean {d.mean().item():7.2f}  p10 {q[0].item():7.2f}  p50 {q[1].item():7.2f}  p90 {q[2].item():7.2f}")
+        d = (t[1:, 11] - t[1:, 5]) / mhz
+        print(f"  first status word after look-back start mean {d.mean().item():.2f}  p10 {torch.quantile(d, 0.1).item():.2f}  p90 {torch.quantile(d, 0.9).item():.2f} us")
         # pass duration and tile start spacing from the global timer
         g = t[:, 0]
         span = (g.max() - g.min()).item() / 1e3

@@ -8,6 +8,7 @@
 // constants so that one kernel instantiation serves unsigned, signed, ascending and
 // descending keys of a given width (floating keys use a second instantiation).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -184,6 +185,24 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// Same, at a compile-time byte offset from `p` (the offset goes into the instruction: no address arithmetic per load).
+template <int OFF>
+__device__ __forceinline__ uint32_t ld_status_at(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1+%2];" : "=r"(v) : "l"(p), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ unsigned long long ld_status_at(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1+%2];" : "=l"(v) : "l"(p), "n"(OFF) : "memory");
+  return v;
+}
+// win[j] = status word of the j-th predecessor row (rows are ROW_BYTES apart), j = 0 .. sizeof...(J) - 1
+template <int ROW_BYTES, typename OffT, int... J>
+__device__ __forceinline__ void load_status_window(const OffT* p, OffT* win, std::integer_sequence<int, J...>) {
+  ((win[J] = ld_status_at<-J * ROW_BYTES>(p)), ...);
+}
 __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -286,6 +305,11 @@ __device__ __forceinline__ uint32_t opaque(uint32_t x) {
 __device__ __forceinline__ unsigned long long opaque(unsigned long long x) {
   asm volatile("" : "+l"(x));
   return x;
+}
+
+// Shared-memory add without a result (reduction form).
+__device__ __forceinline__ void red_shared_add(uint32_t smem_addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
 }
 
 // Leader-only shared-memory fetch-add: returns the old value on the lanes where `pred` holds; the result is

@@ -76,17 +76,28 @@ struct OnesweepSmem {
 //       bit 2 = (experiment) cross-proxy fence before a persistent CTA re-fills its staging buffers;
 //       bit 3 = complement of the ballots on the FMA pipe (IMAD) instead of the ALU pipe (LOP3);
 //       bit 4 = (tuning) thread 0 records the SM clock at every phase boundary into P.trace;
-//       bits 8+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
+//       bit 8 = branch-free look-back window (all LBW words summed with a select chain when every one is published);
+//       bits 12+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
 template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0,
           int MODE = 0>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, OpT> P) {
   constexpr int PERSIST = MODE & 3;
   constexpr bool TRACE = (MODE & 16) != 0;
+  constexpr bool BLOCKID = (MODE & 32) != 0;   // tile id = blockIdx.x (CTAs are dispatched in index order) instead of a claim
+  constexpr bool VAL_LATE = (MODE & 64) != 0;  // staged values -> registers after the look-back (frees registers for its window)
+  // EARLY: tile digit counts come from a cheap counting sweep (one shared-memory reduction per item) and are published BEFORE
+  // the ranking sweep, so successors never wait for a slow ranking phase of this tile; the ranking atomics then run on
+  // counters that already hold absolute positions, which removes the per-item base gather and fuses the key reorder into
+  // the ranking loop.
+  constexpr bool EARLY = (MODE & 128) != 0;
+  constexpr bool FASTLB = (MODE & 256) != 0;
+  static_assert(!(BLOCKID && PERSIST), "persistent CTAs claim their tiles");
+  static_assert(!(EARLY && ABL), "ablations apply to the classic flow");
 #define B2S_TRACE(slot)                                                                  \
   do {                                                                                   \
     if (TRACE && P.trace && threadIdx.x == 0) P.trace[tile * 16 + (slot)] = clock64();   \
   } while (0)
-  constexpr int PFD = MODE >> 8;
+  constexpr int PFD = MODE >> 12;
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
   using ValU = typename UIntOf<VBYTES ? VBYTES : 1>::type;
@@ -115,14 +126,16 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
 
   // ---- P0: claim a tile (launch order == input order), arm the barriers, clear counters
   if (tid == 0) {
-    *s_tile = atomicAdd(P.tile_counter, 1u);
+    if (!BLOCKID) *s_tile = atomicAdd(P.tile_counter, 1u);
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     mbar_fence_init();
   }
+  if (!BLOCKID) {
 #pragma unroll
-  for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
-  __syncthreads();
+    for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
+    __syncthreads();
+  }
 
   const unsigned long long num_tiles = (P.n + TILE - 1) / TILE;
   unsigned int phase = 0;  // parity of the mbarrier phase the next bulk copies complete
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   if (PERSIST) tid = (int)opaque((unsigned int)tid);
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const unsigned long long tile = *s_tile;
+  const unsigned long long tile = BLOCKID ? (unsigned long long)blockIdx.x : (unsigned long long)*s_tile;
   if (PERSIST && tile >= num_tiles) break;
   if (TRACE && P.trace && threadIdx.x == 0) {
     unsigned long long gt;
@@ -199,6 +212,12 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     __syncthreads();
   }
 
+  if (BLOCKID) {  // the tile id needed no round trip: the copies above are already in flight while the counters are cleared
+#pragma unroll
+    for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
+    __syncthreads();
+  }
+
   // ---- P1: keys -> registers (warp-striped rows), match-rank inside the warp
   const int warp_base = warp * 32 * IPT;
   W key[IPT];
@@ -219,6 +238,11 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   //   leader atomic of row u  ->  8 ballot rounds of row u+1 (ALU work while the atomic is in flight)
   //   ->  rank of row u-1 from its broadcast (issued one iteration ago)  ->  SHFL broadcast of row u's atomic.
   // Neither the ATOMS->SHFL nor the SHFL->use latency is exposed; only the shared-memory pipe's throughput is.
+  if (EARLY) {
+    // ---- P1a: counting sweep -- per-warp digit counts, no ranks yet
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) red_shared_add(myhist_s + op(key[u]) * 4, 1u);
+  } else {
   unsigned int d = op(key[0]);
   unsigned int m = match_ballot<RADIX_BITS, (MODE & 8) != 0>(d, P.ones);
   unsigned int bcast_prev = 0, below_prev = 0, d_prev = 0;
@@ -247,20 +271,17 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     m = m_next;
   }
   if (!(ABL & 4)) rk[IPT - 1] = opaque((bcast_prev + below_prev) | (d_prev << 16));
+  }
   __syncthreads();  // S2: all warp histograms complete, all staged keys consumed
   B2S_TRACE(3);  // ranked
 
   // ---- P2: per-digit tile counts -> partial status; digit prefix; per-warp bases
   OffT* status = reinterpret_cast<OffT*>(P.status) + tile * RADIX;
   unsigned int total = 0;
-  unsigned int wcnt[NW];
   if (tid < RADIX) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      wcnt[w] = whist[w * RADIX + tid];
-      total += wcnt[w];
-    }
-    st_status(status + tid, (tile == 0 ? FLAG_INCLUSIVE : FLAG_PARTIAL) | (OffT)total);
+    for (int w = 0; w < NW; ++w) total += whist[w * RADIX + tid];
+    st_status(status + tid, (tile == 0 ? (FLAG_INCLUSIVE | FLAG_PARTIAL) : FLAG_PARTIAL) | (OffT)total);
     if (P.status_next) reinterpret_cast<OffT*>(P.status_next)[tile * RADIX + tid] = 0;
   }
   unsigned int incl = total;
@@ -271,25 +292,58 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   }
   if (tid < RADIX && lane == 31) s_wtot[warp] = incl;
   __syncthreads();  // S2b
-  unsigned int tile_excl = 0;
   if (tid < RADIX) {
     unsigned int base = 0;
 #pragma unroll
     for (int w = 0; w < RADIX / 32; ++w)
       if (w < warp) base += s_wtot[w];
-    tile_excl = base + incl - total;
-    unsigned int run = tile_excl;
+    // the per-warp counts are read a second time rather than kept in NW registers across the barrier, and the digit's
+    // first position in the tile is parked in its s_goff slot until the look-back needs it: registers are what limits
+    // the items per thread
+    unsigned int run = base + incl - total;
+    s_goff[tid] = (OffT)run;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
+      const unsigned int c = whist[w * RADIX + tid];
       whist[w * RADIX + tid] = run;
-      run += wcnt[w];
+      run += c;
     }
   }
   __syncthreads();  // S3: per-warp bases ready
   B2S_TRACE(4);  // digit scan done
 
   // ---- P3: reorder keys in shared memory (staged keys were all consumed before S2)
-  {
+  if (EARLY) {
+    // ranking sweep on counters that hold absolute tile positions: the leader's atomic returns the position of the first
+    // peer, so a key goes to its sorted slot as soon as its row is ranked (same software pipeline as the classic loop)
+    KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
+    unsigned int d = op(key[0]);
+    unsigned int m = match_ballot<RADIX_BITS, (MODE & 8) != 0>(d, P.ones);
+    unsigned int bcast_prev = 0, below_prev = 0;
+#pragma unroll
+    for (int u = 0; u < IPT; ++u) {
+      const unsigned int leader = bfind(m);
+      const unsigned int below = __popc(m & lt);
+      const unsigned int raw = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
+      unsigned int d_next = 0, m_next = 0;
+      if (u + 1 < IPT) {
+        d_next = op(key[u + 1]);
+        m_next = match_ballot<RADIX_BITS, (MODE & 8) != 0>(d_next, P.ones);
+      }
+      if (u > 0) {
+        const unsigned int r = bcast_prev + below_prev;
+        rk[u - 1] = r;
+        sk[r] = (KeyU)key[u - 1];
+      }
+      bcast_prev = __shfl_sync(0xffffffffu, raw, leader);
+      below_prev = below;
+      d = d_next;
+      m = m_next;
+    }
+    const unsigned int r = bcast_prev + below_prev;
+    rk[IPT - 1] = r;
+    sk[r] = (KeyU)key[IPT - 1];
+  } else {
     KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
 #pragma unroll
     for (int u = 0; u < IPT; ++u) {
@@ -300,12 +354,13 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   }
   // values: staged values -> registers (re-using the key registers), barrier, then in-place reorder
   ValU val[HAS_VALUES ? IPT : 1];
-  if (HAS_VALUES) {
+  auto load_values = [&]() {
     if (bulk) mbar_wait(&bar[1], phase);
     const ValU* sv = reinterpret_cast<const ValU*>(stage_v + vshift);
 #pragma unroll
     for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
-  }
+  };
+  if (HAS_VALUES && !VAL_LATE) load_values();
 
   B2S_TRACE(5);  // keys reordered, values in registers
   // ---- look-back: exclusive prefix of this tile for digit `tid`.  Each round trip reads the next LBW
@@ -319,28 +374,71 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       const OffT* p = status - RADIX + tid;  // first entry of the current window
       unsigned long long left = tile;        // predecessors not yet examined
       bool done = false;
+      unsigned int n_trips = 0, n_spins = 0, n_walked = 0;  // TRACE only
+      long long t_first = 0;
       while (true) {
         OffT win[LBW];
+        if (TRACE) ++n_trips;
+        bool handled = false;
+        if (FASTLB && left >= (unsigned long long)LBW) {
+          // common case: the whole window exists and every word in it is published.  An inclusive word carries BOTH flag
+          // bits, so "all published" is one AND-reduction; the sum up to the nearest inclusive word is a select chain
+          // from the far end (no branches, no loads with computed addresses)
+          load_status_window<RADIX * (int)sizeof(OffT)>(p, win, std::make_integer_sequence<int, LBW>{});
+          OffT all = win[0], any = win[0];
 #pragma unroll
-        for (int j = 0; j < LBW; ++j) win[j] = (left > (unsigned long long)j) ? ld_status(p - j * RADIX) : FLAG_INCLUSIVE;
+          for (int j = 1; j < LBW; ++j) {
+            all &= win[j];
+            any |= win[j];
+          }
+          if (all & FLAG_PARTIAL) {
+            OffT acc = 0;
 #pragma unroll
-        for (int j = 0; j < LBW; ++j) {
-          if (!done) {
-            OffT v = win[j];
-            while ((v & (FLAG_INCLUSIVE | FLAG_PARTIAL)) == 0) v = ld_status(p - j * RADIX);
-            excl += v & VALUE_MASK;
-            if (v & FLAG_INCLUSIVE) done = true;
+            for (int j = LBW - 1; j >= 0; --j) {
+              const OffT stop = (win[j] & FLAG_INCLUSIVE) ? ~OffT(0) : OffT(0);
+              acc = (win[j] & VALUE_MASK) + (acc & ~stop);
+            }
+            excl += acc;
+            if (TRACE) n_walked += LBW;
+            if (TRACE && n_trips == 1) t_first = clock64();
+            done = (any & FLAG_INCLUSIVE) != 0;
+            handled = true;
+          }
+        }
+        if (!handled) {
+#pragma unroll
+          for (int j = 0; j < LBW; ++j) win[j] = (left > (unsigned long long)j) ? ld_status(p - j * RADIX) : FLAG_INCLUSIVE;
+#pragma unroll
+          for (int j = 0; j < LBW; ++j) {
+            if (!done) {
+              OffT v = win[j];
+              while ((v & (FLAG_INCLUSIVE | FLAG_PARTIAL)) == 0) {
+                v = ld_status(p - j * RADIX);
+                if (TRACE) ++n_spins;
+              }
+              if (TRACE) ++n_walked;
+              if (TRACE && n_trips == 1 && j == 0) t_first = clock64();
+              excl += v & VALUE_MASK;
+              if (v & FLAG_INCLUSIVE) done = true;
+            }
           }
         }
         if (done) break;
         p -= LBW * RADIX;
         left -= LBW;
       }
-      st_status(status + tid, FLAG_INCLUSIVE | (excl + (OffT)total));
+      st_status(status + tid, FLAG_INCLUSIVE | FLAG_PARTIAL | (excl + (OffT)total));
+      if (TRACE && P.trace && tid == 0) {
+        P.trace[tile * 16 + 12] = n_trips;
+        P.trace[tile * 16 + 13] = n_spins;
+        P.trace[tile * 16 + 14] = n_walked;
+        P.trace[tile * 16 + 11] = (unsigned long long)t_first;  // overwrites the entry stamp: first status word in hand
+      }
     }
-    s_goff[tid] = reinterpret_cast<const OffT*>(P.bins)[tid] + excl - (OffT)tile_excl;
+    s_goff[tid] = reinterpret_cast<const OffT*>(P.bins)[tid] + excl - s_goff[tid];
   }
   B2S_TRACE(6);  // look-back of digit 0 done
+  if (HAS_VALUES && VAL_LATE) load_values();
   if (HAS_VALUES) {
     __syncthreads();  // S3b: every staged value is in a register
     B2S_TRACE(7);  // everybody's look-back done

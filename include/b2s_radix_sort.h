@@ -116,7 +116,7 @@ int b2s_set_variant(int variant);
 int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int *threads, int *items_per_thread,
                          int *min_ctas_per_sm, int *match_mode);
 /* Scheduling mode of a variant: bits 0-1 = 0 one tile per CTA, 1/2 persistent CTAs (next tile claimed after/before the
- * write-out); bits 8+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
+ * write-out); bits 12+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
 int b2s_variant_mode(int key_bytes, int value_bytes, int variant);
 /* Tuning builds: digit pass number `pass` of every following sort writes per-tile phase timestamps (u64[tiles][16], SM clock
  * cycles; slot 0 = global timer in ns, slot 15 = SM id) to d_trace when the active variant is a trace variant.  NULL disables. */
