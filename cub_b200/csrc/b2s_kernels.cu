@@ -24,7 +24,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 108;
+constexpr int NUM_VARIANTS = 28;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -48,127 +48,45 @@ constexpr Variant variant_cfg(int vi) {
   // transform needs registers) and pairs take fewer items per thread than integer keys alone.
   constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 12);
   const bool small_pairs = V > 0 && K + V <= 8;
-  const Variant d = V == 0       ? Variant{384, scale_ipt<V>(F ? 20 : 22), 3, 16, 0, M}
-                    : small_pairs ? Variant{384, scale_ipt<V>(F ? 17 : 19), 3, 12, 0, M}
+  const Variant d = V == 0       ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
+                    : small_pairs ? Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M}
                                   : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M};
 #ifdef B2S_TUNING
   switch (vi) {
     case 0: return d;
-    case 1: return Variant{512, scale_ipt<V>(20), 2, 4};
-    case 2: return Variant{512, scale_ipt<V>(20), 2, 2};
-    case 3: return Variant{512, scale_ipt<V>(20), 2, 8};
-    case 4: return Variant{512, scale_ipt<V>(16), 2, 4};
-    case 5: return Variant{384, scale_ipt<V>(16), 3, 4};
-    case 6: return Variant{384, scale_ipt<V>(19), 3, 4};
-    case 7: return Variant{512, scale_ipt<V>(22), 2, 4};
-    case 8: return Variant{256, scale_ipt<V>(16), 4, 4};
-    case 9: return Variant{256, scale_ipt<V>(20), 4, 4};
-    case 10: return Variant{1024, scale_ipt<V>(16), 1, 4};
-    case 11: return Variant{512, scale_ipt<V>(18), 2, 4};
-    // timing-only ablations of the production point (wrong results by design): see ABL in b2s_onesweep.cuh
-    case 12: return Variant{512, scale_ipt<V>(20), 2, 4, 1};
-    case 13: return Variant{512, scale_ipt<V>(20), 2, 4, 2};
-    case 14: return Variant{512, scale_ipt<V>(20), 2, 4, 4};
-    case 15: return Variant{512, scale_ipt<V>(20), 2, 4, 8};
-    case 16: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 2};
-    case 17: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 8};
-    // L2 prefetch distance / persistent CTAs (see MODE in b2s_onesweep.cuh)
-    case 18: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 296 << 12};
-    case 19: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 592 << 12};
-    case 20: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 74 << 12};
-    case 21: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1};
-    case 22: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2};
-    case 23: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1 | 4};
-    case 24: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2 | 4};
-    case 25: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 222 << 12};
-    case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 1};
-    case 27: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 2};
-    case 28: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 148 << 12};
-    case 29: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 1};
-    case 30: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 2};
-    case 31: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 8};
-    case 32: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 8 | (148 << 12)};
-    case 33: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | (222 << 12)};
-    case 34: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 8 | (148 << 12)};
-    case 35: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2 | 8};
-    // phase-timestamp traces (bit 4)
-    case 36: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16};
-    case 37: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 1};
-    case 38: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16};
-    case 39: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 16};
-    // wider look-back windows, block-index tile ids (bit 5), late value loads (bit 6); all with IMAD complement + prefetch
-    case 40: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 8 | (148 << 12)};
-    case 41: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | (148 << 12)};
-    case 42: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 8 | 64 | (148 << 12)};
-    case 43: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 64 | (148 << 12)};
-    case 44: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 8 | 32 | (148 << 12)};
-    case 45: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 8 | 32 | 64 | (148 << 12)};
-    case 46: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 32 | 64 | (148 << 12)};
-    case 47: return Variant{384, scale_ipt<V>(19), 3, 8, 0, 8 | (222 << 12)};
-    case 48: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 8 | 64 | (222 << 12)};
-    case 49: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | 32 | (222 << 12)};
-    case 50: return Variant{384, scale_ipt<V>(19), 3, 8, 0, 8 | 32 | 64 | (222 << 12)};
-    case 51: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 8 | 32 | 64 | (222 << 12)};
-    case 52: return Variant{512, scale_ipt<V>(20), 2, 8, 0, 8 | 32 | 64 | (148 << 12)};
-    case 53: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 8 | 32 | (148 << 12)};
-    // traces of the candidates
-    case 54: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 16 | 8 | 32 | 64 | (148 << 12)};
-    case 55: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 8 | (148 << 12)};
-    // early counts (bit 7) with wide single-shot look-back windows
-    case 56: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 128 | 8 | (148 << 12)};
-    case 57: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 128 | 8 | (148 << 12)};
-    case 58: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 128 | 8 | 64 | (148 << 12)};
-    case 59: return Variant{256, scale_ipt<V>(20), 4, 32, 0, 128 | 8 | 64 | (148 << 12)};
-    case 60: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 128 | 8 | 32 | 64 | (148 << 12)};
-    case 61: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 128 | 8 | (222 << 12)};
-    case 62: return Variant{384, scale_ipt<V>(19), 3, 8, 0, 128 | 8 | (222 << 12)};
-    case 63: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 128 | 8 | 64 | (222 << 12)};
-    case 64: return Variant{384, scale_ipt<V>(19), 3, 32, 0, 128 | 8 | 64 | (222 << 12)};
-    case 65: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 128 | 8 | 32 | 64 | (222 << 12)};
-    case 66: return Variant{512, scale_ipt<V>(20), 2, 8, 0, 128 | 8 | (148 << 12)};
-    case 67: return Variant{512, scale_ipt<V>(20), 2, 16, 0, 128 | 8 | 64 | (148 << 12)};
-    case 68: return Variant{256, scale_ipt<V>(22), 4, 16, 0, 128 | 8 | 64 | (148 << 12)};
-    case 69: return Variant{384, scale_ipt<V>(20), 3, 16, 0, 128 | 8 | 64 | (222 << 12)};
-    case 70: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 16 | 128 | 8 | 64 | (148 << 12)};
-    case 71: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 128 | 8 | (148 << 12)};
-    // branch-free look-back windows (bit 8)
-    case 72: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 256 | 8 | (148 << 12)};
-    case 73: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 256 | 8 | (148 << 12)};
-    case 74: return Variant{256, scale_ipt<V>(20), 4, 12, 0, 256 | 8 | 64 | (148 << 12)};
-    case 75: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 256 | 8 | 64 | (148 << 12)};
-    case 76: return Variant{256, scale_ipt<V>(20), 4, 24, 0, 256 | 8 | 64 | (148 << 12)};
-    case 77: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 256 | 8 | 32 | 64 | (148 << 12)};
-    case 78: return Variant{384, scale_ipt<V>(19), 3, 8, 0, 256 | 8 | (222 << 12)};
-    case 79: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 256 | 8 | 64 | (222 << 12)};
-    case 80: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 256 | 8 | 64 | (222 << 12)};
-    case 81: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 256 | 8 | 32 | 64 | (222 << 12)};
-    case 82: return Variant{512, scale_ipt<V>(20), 2, 8, 0, 256 | 8 | (148 << 12)};
-    case 83: return Variant{512, scale_ipt<V>(20), 2, 12, 0, 256 | 8 | 64 | (148 << 12)};
-    case 84: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 256 | 128 | 8 | 64 | (148 << 12)};
-    case 85: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 86: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 16 | 256 | 8 | 64 | (148 << 12)};
-    case 87: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 16 | 256 | 8 | (148 << 12)};
-    // early counts + branch-free window: neighbourhood of variant 85
-    case 88: return Variant{384, scale_ipt<V>(19), 3, 8, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 89: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 90: return Variant{384, scale_ipt<V>(19), 3, 24, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 91: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 256 | 128 | 8 | 64 | 32 | (222 << 12)};
-    case 92: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 256 | 128 | 8 | 64 | 32 | (222 << 12)};
-    case 93: return Variant{384, scale_ipt<V>(20), 3, 16, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 94: return Variant{384, scale_ipt<V>(21), 3, 16, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 95: return Variant{384, scale_ipt<V>(22), 3, 16, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 96: return Variant{512, scale_ipt<V>(20), 2, 8, 0, 256 | 128 | 8 | 64 | (148 << 12)};
-    case 97: return Variant{512, scale_ipt<V>(20), 2, 12, 0, 256 | 128 | 8 | 64 | (148 << 12)};
-    case 98: return Variant{512, scale_ipt<V>(20), 2, 16, 0, 256 | 128 | 8 | 64 | (148 << 12)};
-    case 99: return Variant{256, scale_ipt<V>(20), 4, 8, 0, 256 | 128 | 8 | 64 | (148 << 12)};
-    case 100: return Variant{256, scale_ipt<V>(20), 4, 12, 0, 256 | 128 | 8 | 64 | (148 << 12)};
-    case 101: return Variant{256, scale_ipt<V>(20), 4, 12, 0, 256 | 128 | 8 | 64 | 32 | (148 << 12)};
-    case 102: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 256 | 128 | 8 | 64 | (111 << 12)};
-    case 103: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 256 | 128 | 8 | 64 | (444 << 12)};
-    case 104: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 256 | 128 | 8 | (222 << 12)};
-    case 105: return Variant{320, scale_ipt<V>(20), 3, 16, 0, 256 | 128 | 8 | 64 | (222 << 12)};
-    case 106: return Variant{384, scale_ipt<V>(19), 3, 16, 0, 16 | 256 | 128 | 8 | 64 | (222 << 12)};
-    case 107: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16 | 8 | (222 << 12)};
+    // the kernel as it stood at the start of this series (classic flow: ranking produces the counts, serial LBW=4 walk)
+    case 1: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 0};
+    case 2: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 0};
+    case 3: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 0};
+    // timing-only ablations of variant 1 (wrong results by design): see ABL in b2s_onesweep.cuh
+    case 4: return Variant{512, scale_ipt<V>(20), 2, 4, 1, 0};
+    case 5: return Variant{512, scale_ipt<V>(20), 2, 4, 2, 0};
+    case 6: return Variant{512, scale_ipt<V>(20), 2, 4, 4, 0};
+    case 7: return Variant{512, scale_ipt<V>(20), 2, 4, 8, 0};
+    case 8: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 2, 0};
+    case 9: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 8, 0};
+    // the ladder from variant 3 to production, one technique at a time (MODE bits in b2s_onesweep.cuh)
+    case 10: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 222 << 12};                            // + L2 prefetch
+    case 11: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | (222 << 12)};                      // + IMAD complement
+    case 12: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 256 | (222 << 12)};          // + branch-free window of 12
+    case 13: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 128 | 256 | (222 << 12)};    // + early counts
+    case 14: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 32 | 64 | 128 | 256 | (222 << 12)};  // + block-index tile ids
+    // neighbours of the production point
+    case 15: return Variant{384, scale_ipt<V>(20), 3, 8, 0, M};
+    case 16: return Variant{384, scale_ipt<V>(20), 3, 16, 0, M};
+    case 17: return Variant{384, scale_ipt<V>(22), 3, 12, 0, M};
+    case 18: return Variant{384, scale_ipt<V>(24), 3, 12, 0, M};
+    case 19: return Variant{512, scale_ipt<V>(22), 2, 12, 0, M};
+    case 20: return Variant{512, scale_ipt<V>(20), 2, 12, 0, M};
+    case 21: return Variant{256, scale_ipt<V>(20), 4, 8, 0, M};
+    // rejected: persistent CTAs (the tile loop makes the ranking sweep spill), serial wide window, unfenced early claim
+    case 22: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1};
+    case 23: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2};
+    case 24: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 64 | (148 << 12)};
+    // phase-timestamp traces (bench/trace.py): old production, classic 384, production
+    case 25: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16};
+    case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16};
+    case 27: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 16 | (M & ~(222 << 12)) | (222 << 12)};
     default: return d;
   }
 #else
