@@ -68,11 +68,11 @@ def main():
             q = torch.quantile(d, torch.tensor([0.1, 0.5, 0.9], dtype=torch.double))
             rec["phases_us"][name] = {"mean": d.mean().item(), "p10": q[0].item(), "p50": q[1].item(), "p90": q[2].item()}
             print(f"  {name:38s} mean {d.mean().item():7.2f}  p10 {q[0].item():7.2f}  p50 {q[1].item():7.2f}  p90 {q[2].item():7.2f} us")
-        for name, slot in (("look-back round trips", 12), ("look-back spin reloads", 13), ("predecessors summed", 14)):
+        for name, slot in () if not (rec["mode"] & 512) else (("look-back round trips", 12), ("look-back spin reloads", 13), ("predecessors summed", 14)):
             d = t[1:, slot]
             q = torch.quantile(d, torch.tensor([0.1, 0.5, 0.9], dtype=torch.double))
             print(f"  {name:38s} mean {d.mean().item():7.2f}  p10 {q[0].item():7.2f}  p50 {q[1].item():7.2f}  p90 {q[2].item():7.2f}")
-        d = (t[1:, 11] - t[1:, 5]) / mhz
+        d = (t[1:, 11] - t[1:, 5]) / mhz if (rec["mode"] & 512) else torch.zeros(1, dtype=torch.double)
         print(f"  first status word after look-back start mean {d.mean().item():.2f}  p10 {torch.quantile(d, 0.1).item():.2f}  p90 {torch.quantile(d, 0.9).item():.2f} us")
         # pass duration and tile start spacing from the global timer
         g = t[:, 0]

@@ -24,7 +24,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 28;
+constexpr int NUM_VARIANTS = 29;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -49,6 +49,7 @@ constexpr Variant variant_cfg(int vi) {
   constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 12);
   const bool small_pairs = V > 0 && K + V <= 8;
   const Variant d = V == 0       ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
+                    : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
                     : small_pairs ? Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M}
                                   : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M};
 #ifdef B2S_TUNING
@@ -84,9 +85,10 @@ constexpr Variant variant_cfg(int vi) {
     case 23: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2};
     case 24: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 64 | (148 << 12)};
     // phase-timestamp traces (bench/trace.py): old production, classic 384, production
-    case 25: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16};
-    case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16};
-    case 27: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 16 | (M & ~(222 << 12)) | (222 << 12)};
+    case 25: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 512};
+    case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16 | 512};
+    case 27: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 16 | d.mode};          // production, time stamps only
+    case 28: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 16 | 512 | d.mode};    // + look-back statistics (spills)
     default: return d;
   }
 #else

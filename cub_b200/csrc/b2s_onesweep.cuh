@@ -66,7 +66,7 @@ struct OnesweepSmem {
   static constexpr int OFF_WHIST = OFF_VALS + (VAL_BYTES + 127) / 128 * 128;
   static constexpr int OFF_GOFF = OFF_WHIST + NW * RADIX * 4;
   static constexpr int OFF_MISC = OFF_GOFF + RADIX * 8;
-  static constexpr int TOTAL = OFF_MISC + 128;
+  static constexpr int TOTAL = OFF_MISC + 256;  // barriers, scan partials, tile id; +128: phase stamps of the trace variants
 };
 
 // ABL: timing-only ablation switches for bench/tune.py (results are WRONG when non-zero; never used by the product):
@@ -77,12 +77,14 @@ struct OnesweepSmem {
 //       bit 3 = complement of the ballots on the FMA pipe (IMAD) instead of the ALU pipe (LOP3);
 //       bit 4 = (tuning) thread 0 records the SM clock at every phase boundary into P.trace;
 //       bit 8 = branch-free look-back window (all LBW words summed with a select chain when every one is published);
+//       bit 9 = (tuning, with bit 4) look-back statistics in trace slots 11-14;
 //       bits 12+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
 template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0,
           int MODE = 0>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, OpT> P) {
   constexpr int PERSIST = MODE & 3;
   constexpr bool TRACE = (MODE & 16) != 0;
+  constexpr bool TRACE_LB = TRACE && (MODE & 512) != 0;  // also count the look-back's round trips / words (costs registers)
   constexpr bool BLOCKID = (MODE & 32) != 0;   // tile id = blockIdx.x (CTAs are dispatched in index order) instead of a claim
   constexpr bool VAL_LATE = (MODE & 64) != 0;  // staged values -> registers after the look-back (frees registers for its window)
   // EARLY: tile digit counts come from a cheap counting sweep (one shared-memory reduction per item) and are published BEFORE
@@ -93,9 +95,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   constexpr bool FASTLB = (MODE & 256) != 0;
   static_assert(!(BLOCKID && PERSIST), "persistent CTAs claim their tiles");
   static_assert(!(EARLY && ABL), "ablations apply to the classic flow");
-#define B2S_TRACE(slot)                                                                  \
-  do {                                                                                   \
-    if (TRACE && P.trace && threadIdx.x == 0) P.trace[tile * 16 + (slot)] = clock64();   \
+  // stamps go to shared memory (fixed address, no registers held) and are copied out once per tile
+#define B2S_TRACE(slot)                                                                                      \
+  do {                                                                                                       \
+    if (TRACE && threadIdx.x == 0) reinterpret_cast<long long*>(smem + L::OFF_MISC + 128)[slot] = clock64(); \
   } while (0)
   constexpr int PFD = MODE >> 12;
   using KeyU = typename UIntOf<KBYTES>::type;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   unsigned int* s_tile = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 64);
 
   int tid = threadIdx.x;
-  long long t_entry = TRACE ? clock64() : 0;
+  B2S_TRACE(11);  // CTA entry
 
   // ---- P0: claim a tile (launch order == input order), arm the barriers, clear counters
   if (tid == 0) {
@@ -147,15 +150,14 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   const int warp = tid >> 5;
   const unsigned long long tile = BLOCKID ? (unsigned long long)blockIdx.x : (unsigned long long)*s_tile;
   if (PERSIST && tile >= num_tiles) break;
-  if (TRACE && P.trace && threadIdx.x == 0) {
+  if (TRACE && threadIdx.x == 0) {
     unsigned long long gt;
     unsigned int smid;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    P.trace[tile * 16 + 0] = gt;
-    P.trace[tile * 16 + 15] = smid;
+    reinterpret_cast<unsigned long long*>(smem + L::OFF_MISC + 128)[0] = gt;
+    reinterpret_cast<unsigned long long*>(smem + L::OFF_MISC + 128)[15] = smid;
   }
-  if (TRACE && P.trace && threadIdx.x == 0) P.trace[tile * 16 + 11] = (unsigned long long)t_entry;  // CTA entry / previous tile done
   B2S_TRACE(1);  // tile claimed
   const unsigned long long tile_base = tile * TILE;
   const unsigned long long remain = P.n - tile_base;
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       long long t_first = 0;
       while (true) {
         OffT win[LBW];
-        if (TRACE) ++n_trips;
+        if (TRACE_LB) ++n_trips;
         bool handled = false;
         if (FASTLB && left >= (unsigned long long)LBW) {
           // common case: the whole window exists and every word in it is published.  An inclusive word carries BOTH flag
@@ -399,8 +401,8 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
               acc = (win[j] & VALUE_MASK) + (acc & ~stop);
             }
             excl += acc;
-            if (TRACE) n_walked += LBW;
-            if (TRACE && n_trips == 1) t_first = clock64();
+            if (TRACE_LB) n_walked += LBW;
+            if (TRACE_LB && n_trips == 1) t_first = clock64();
             done = (any & FLAG_INCLUSIVE) != 0;
             handled = true;
           }
@@ -414,10 +416,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
               OffT v = win[j];
               while ((v & (FLAG_INCLUSIVE | FLAG_PARTIAL)) == 0) {
                 v = ld_status(p - j * RADIX);
-                if (TRACE) ++n_spins;
+                if (TRACE_LB) ++n_spins;
               }
-              if (TRACE) ++n_walked;
-              if (TRACE && n_trips == 1 && j == 0) t_first = clock64();
+              if (TRACE_LB) ++n_walked;
+              if (TRACE_LB && n_trips == 1 && j == 0) t_first = clock64();
               excl += v & VALUE_MASK;
               if (v & FLAG_INCLUSIVE) done = true;
             }
@@ -428,11 +430,12 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
         left -= LBW;
       }
       st_status(status + tid, FLAG_INCLUSIVE | FLAG_PARTIAL | (excl + (OffT)total));
-      if (TRACE && P.trace && tid == 0) {
-        P.trace[tile * 16 + 12] = n_trips;
-        P.trace[tile * 16 + 13] = n_spins;
-        P.trace[tile * 16 + 14] = n_walked;
-        P.trace[tile * 16 + 11] = (unsigned long long)t_first;  // overwrites the entry stamp: first status word in hand
+      if (TRACE_LB && tid == 0) {
+        unsigned long long* tr = reinterpret_cast<unsigned long long*>(smem + L::OFF_MISC + 128);
+        tr[12] = n_trips;
+        tr[13] = n_spins;
+        tr[14] = n_walked;
+        tr[11] = (unsigned long long)t_first;  // overwrites the entry stamp: first status word in hand
       }
     }
     s_goff[tid] = reinterpret_cast<const OffT*>(P.bins)[tid] + excl - s_goff[tid];
@@ -484,6 +487,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     }
   }
   B2S_TRACE(9);  // thread 0's stores issued
+  if (TRACE && P.trace && threadIdx.x == 0 && !PERSIST) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) P.trace[tile * 16 + i] = reinterpret_cast<unsigned long long*>(smem + L::OFF_MISC + 128)[i];
+  }
   if (!PERSIST) break;
   // ---- next tile of a persistent CTA: claim, clear the warp counters (unused since P3); the barrier also orders the
   // write-out's reads of the staging buffers before the next TMA copies into them
@@ -493,7 +500,11 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   phase ^= bulk_flag;
   __syncthreads();
   B2S_TRACE(10);  // everybody's stores issued, next tile claimed
-  if (TRACE) t_entry = clock64();
+  if (TRACE && P.trace && threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) P.trace[tile * 16 + i] = reinterpret_cast<unsigned long long*>(smem + L::OFF_MISC + 128)[i];
+  }
+  B2S_TRACE(11);
   }  // tile loop
 #undef B2S_TRACE
 }
