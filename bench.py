@@ -201,6 +201,8 @@ def run_ours(a):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION/INFO) go to stderr: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     b2s = _lib.load()
     n = 1 << int(os.environ.get("B2S_BENCH_LOG2N", "28"))

@@ -4,6 +4,7 @@ Layout:
   csrc/                 hand-written CUDA kernels + the C-ABI (include/b2s_radix_sort.h)
   device_radix_sort.py  host-side mirror of cub::DeviceRadixSort (same entry points / argument meaning)
   multi_gpu.py          single-box multi-GPU SortPairs (one process per GPU, NCCL all-to-all)
+  frontend.py           Thrust-style in-place sort / sort_by_key and the torch.ops.cub_b200.* custom operators
 """
 from .device_radix_sort import (  # noqa: F401
     DeviceRadixSort,
@@ -15,7 +16,14 @@ from .device_radix_sort import (  # noqa: F401
     sort_pairs_host,
 )
 
+from .frontend import sort, sort_by_key, sort_with_indices, stable_sort, stable_sort_by_key  # noqa: E402,F401
+
 __all__ = [
+    "sort",
+    "sort_by_key",
+    "stable_sort",
+    "stable_sort_by_key",
+    "sort_with_indices",
     "DeviceRadixSort",
     "DoubleBuffer",
     "KEY_TYPES",
