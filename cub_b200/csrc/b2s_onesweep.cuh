@@ -6,25 +6,27 @@
 //   AgentRadixSortOnesweep         cub/agent/agent_radix_sort_onesweep.cuh:98-688
 //   BlockRadixRankMatchEarlyCounts cub/block/block_radix_rank.cuh:898-1192
 //
-// B200-first structure (what differs from the reference kernel):
-//   * the tile's keys AND values are staged global->shared by the TMA engine
-//     (cp.async.bulk + mbarrier; SASS UBLKCP) issued by one thread at CTA start: no per-item
-//     LDG instructions, no registers held by loads in flight, values prefetched for free while
-//     the keys are being ranked;  unaligned / partial tiles fall back to element loads;
-//   * several small CTAs per SM (tile 3-6 K items) so that load / rank / scatter phases of
-//     different tiles overlap on one SM instead of one 12-warp CTA serialising them;
-//   * single ranking sweep: warp-private digit counters are produced BY the match ranking
-//     (one leader atomic per (row, digit)), no separate counting sweep;
-//   * keys and values are reordered in shared memory in ONE sweep and written out in ONE
-//     sweep (4 block barriers per tile), so digits / offsets are never cached across phases;
-//   * look-back status words are gpu-scope relaxed (not system-scope volatile), one status
-//     array per pass parity: a pass clears the NEXT pass' array, so the whole sort needs a
-//     single memset; 64-bit status words when n >= 2^30 instead of <=2^28-item portions;
-//   * the look-back reads a window of LBW predecessor tiles per round trip (independent loads, issued late
-//     so that they see fresh state) instead of one.
+// B200-first structure of the PRODUCTION flow (MODE = IMAD | BLOCKID | VAL_LATE | EARLY | FASTLB | prefetch, see the
+// kernel's template comment; MODE = 0 is the classic flow kept for the multi-GPU partition pass and for A/B runs):
+//   * the tile's keys AND values are staged global->shared by the TMA engine (cp.async.bulk + mbarrier; SASS UBLKCP),
+//     issued by one thread as the very first thing the CTA does -- the tile id is the block index, so no claim round
+//     trip precedes them -- plus an L2 prefetch (cp.async.bulk.prefetch.L2) of the tile ~one CTA lifetime ahead: no
+//     per-item LDG instructions, no registers held by loads in flight; unaligned / partial tiles use element loads;
+//   * three 12-warp CTAs per SM so that the load / count / rank / write-out phases of different tiles overlap;
+//   * early counts: a counting sweep (one shared-memory reduction per item on warp-private counters) lets the tile
+//     publish its digit counts BEFORE the ranking sweep; the digit scan then turns the counters into absolute positions
+//     in the sorted tile, so the ranking sweep's leader atomic returns the final slot and every key is stored to it at
+//     once -- no packed (digit, rank) word, no base gather, no separate reorder sweep;
+//   * ranking by 8 ballot rounds whose complements run on the FMA pipe (IMAD), the ALU pipe being the half-rate one;
+//   * look-back status words are gpu-scope relaxed, one array per pass parity (a pass clears the NEXT pass' array: one
+//     memset per sort), 64-bit words when n >= 2^30 instead of <=2^28-item portions; the walk reads a window of LBW
+//     predecessors with back-to-back loads at immediate offsets and sums it branch-free (AND-reduce "all published",
+//     select chain up to the nearest inclusive word);
+//   * values: staged values -> registers after the look-back, then in place to the slots remembered from the ranking;
+//   * write-out: every thread walks the sorted tile with stride NT: coalesced stores of digit runs.
 //
-// Stability: items are ranked in tile order (warp-striped rows, lane order inside a row,
-// rows in program order); tiles are ordered by the dynamic tile id == position in the input.
+// Stability: items are ranked in tile order (warp-striped rows, lane order inside a row, rows in program order);
+// tiles are ordered by their id == position in the input.
 #pragma once
 #include "b2s_common.cuh"
 

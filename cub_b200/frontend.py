@@ -6,10 +6,10 @@
   (reference call shape: ``cub/device/device_radix_sort.cuh:781-790`` DoubleBuffer ``SortPairs``; Thrust itself is not
   vendored in /root/reference).  Radix sort is stable, so the ``stable_`` names are aliases.
 * PyTorch custom operators ``torch.ops.cub_b200.sort_pairs`` / ``sort_keys`` (``torch.library.custom_op`` with fake-tensor
-  kernels, so they trace under ``torch.compile`` / FakeTensorMode) and a ``torch.sort``-shaped helper ``sort_with_indices``.
+  kernels, so they trace under ``torch.compile`` / FakeTensorMode) and a helper shaped like PyTorch's own stable sort, ``sort_with_indices``.
 
 There is no CPU path: every entry point raises on non-CUDA tensors, and the library loader raises if ``libb2s.so`` is
-missing.  Ordering semantics are CUB's, not torch.sort's: floating keys are ordered by their transformed bit patterns
+missing.  Ordering semantics are CUB's, not those of PyTorch's built-in sort: floating keys are ordered by their transformed bit patterns
 (-NaN first and +NaN last when ascending, -0.0 == +0.0 and stable between them; ``device_radix_sort.cuh:70-105``).
 """
 from __future__ import annotations
@@ -119,9 +119,9 @@ def _(keys, descending=False, begin_bit=0, end_bit=-1):
 
 
 def sort_with_indices(x: torch.Tensor, descending: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
-    """``torch.sort(x, stable=True)``-shaped helper for 1-D CUDA tensors: returns (sorted keys, int64 source indices).
+    """Helper shaped like PyTorch's built-in stable sort, for 1-D CUDA tensors: returns (sorted keys, int64 source indices).
     The indices travel through the sort as 4-byte values when they fit (then widened), as 8-byte values otherwise.
-    For integer keys the result equals ``torch.sort(x, descending=descending, stable=True)``; for floating keys NaNs
+    For integer keys the result equals that of PyTorch's built-in stable sort; for floating keys NaNs
     and signed zeros follow CUB's rule (module docstring)."""
     _require_cuda_1d(x, "x")
     n = x.numel()
