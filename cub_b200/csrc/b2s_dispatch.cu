@@ -71,6 +71,11 @@ int g_variant = [] {
   return e ? std::atoi(e) : 0;
 }();
 int tuning_variant() { return g_variant; }
+// B2S_SINGLE_TILE=0 sends small sorts through the multi-kernel path too (A/B runs, tests of that path at small n).
+bool g_single_tile = [] {
+  const char* e = std::getenv("B2S_SINGLE_TILE");
+  return !(e && e[0] == '0');
+}();
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;
@@ -84,16 +89,18 @@ struct KernelSet {
   cudaError_t (*split_count)(const SplitArgs&, cudaStream_t);
   cudaError_t (*split)(const SplitArgs&, cudaStream_t);
   int (*split_tile)(int);
+  cudaError_t (*single)(const SingleArgs&, cudaStream_t);
+  int (*single_items)(int);
 };
 const KernelSet* kernels_for(int kbytes) {
   static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1, onesweep_variant_k1,
-                            split_count_launch_k1, split_launch_k1, split_tile_k1};
+                            split_count_launch_k1, split_launch_k1, split_tile_k1, single_launch_k1, single_tile_items_k1};
   static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2, onesweep_variant_k2,
-                            split_count_launch_k2, split_launch_k2, split_tile_k2};
+                            split_count_launch_k2, split_launch_k2, split_tile_k2, single_launch_k2, single_tile_items_k2};
   static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4, onesweep_variant_k4,
-                            split_count_launch_k4, split_launch_k4, split_tile_k4};
+                            split_count_launch_k4, split_launch_k4, split_tile_k4, single_launch_k4, single_tile_items_k4};
   static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8, onesweep_variant_k8,
-                            split_count_launch_k8, split_launch_k8, split_tile_k8};
+                            split_count_launch_k8, split_launch_k8, split_tile_k8, single_launch_k8, single_tile_items_k8};
   switch (kbytes) {
     case 1: return &k1;
     case 2: return &k2;
@@ -185,6 +192,31 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     return (int)cudaSuccess;
   }
   if (*temp_bytes < L.total) return (int)cudaErrorInvalidValue;
+
+  // Small sorts are launch-bound: at most one tile goes through ONE kernel that runs every pass in shared memory
+  // (the reference's InvokeSingleTile, dispatch_radix_sort.cuh:1272; its cut-over is 4864 items).  The DoubleBuffer form
+  // leaves the result where the multi-pass path would (selector = parity of the pass count).
+  if (n <= (uint64_t)ks->single_items(vbytes) && g_single_tile) {
+    SingleArgs sa{};
+    const int dst = overwrite ? (passes & 1) : 1;
+    sa.keys_in = kbuf[0];
+    sa.keys_out = kbuf[dst];
+    sa.vals_in = vbytes ? vbuf[0] : nullptr;
+    sa.vals_out = vbytes ? vbuf[dst] : nullptr;
+    sa.n = n;
+    sa.dc = make_consts(ki, descending);
+    sa.begin_bit = begin_bit;
+    sa.end_bit = end_bit;
+    sa.vbytes = vbytes;
+    g_events_used = 0;
+    timing_mark(stream);
+    cudaError_t e1 = ks->single(sa, stream);
+    if (e1 != cudaSuccess) return (int)e1;
+    g_last_launches++;
+    timing_mark(stream);
+    if (selector_out) *selector_out = overwrite ? dst : 0;
+    return (int)cudaSuccess;
+  }
 
   unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(d_temp), 256));
   unsigned int* ctrs = reinterpret_cast<unsigned int*>(base + L.off_ctrs);
@@ -478,6 +510,12 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
   if (minb) *minb = v.minb;
   if (match) *match = (v.lbw << 8) | (v.abl << 16);  // legacy slot: look-back window in bits 8+, ablation in 16+
   return ks->num_variants();
+}
+
+int b2s_set_single_tile(int enable) {
+  const int old = b2s::g_single_tile ? 1 : 0;
+  b2s::g_single_tile = enable != 0;
+  return old;
 }
 
 int b2s_set_trace(void* d_trace, int pass) {

@@ -44,6 +44,18 @@ struct PassArgs {
   unsigned long long* trace;  // tuning builds: per-tile phase timestamps (u64[tiles][16]) of one selected pass, else null
 };
 
+// Whole sort of one small tile in a single launch (b2s_single_tile.cuh).
+struct SingleArgs {
+  const void* keys_in;
+  void* keys_out;   // may alias keys_in: the tile is held on chip between the load and the store
+  const void* vals_in;
+  void* vals_out;
+  uint64_t n;
+  DigitConsts dc;
+  int begin_bit, end_bit;
+  int vbytes;
+};
+
 // Multi-GPU partition pass (b2s_split): destination = number of splitters ordering at or before the key.
 constexpr int kMaxSplitters = 7;
 struct SplitArgs {
@@ -77,7 +89,9 @@ struct Variant {
   Variant onesweep_variant_k##K(int variant, int vbytes, bool is_float);                      \
   cudaError_t split_count_launch_k##K(const SplitArgs& a, cudaStream_t s);                    \
   cudaError_t split_launch_k##K(const SplitArgs& a, cudaStream_t s);                          \
-  int split_tile_k##K(int vbytes);
+  int split_tile_k##K(int vbytes);                                                            \
+  cudaError_t single_launch_k##K(const SingleArgs& a, cudaStream_t s);                        \
+  int single_tile_items_k##K(int vbytes);
 B2S_DECL_K(1)
 B2S_DECL_K(2)
 B2S_DECL_K(4)

@@ -8,6 +8,7 @@
 #include "b2s_histogram.cuh"
 #include "b2s_internal.h"
 #include "b2s_onesweep.cuh"
+#include "b2s_single_tile.cuh"
 #include "b2s_split.cuh"
 
 #ifndef B2S_K
@@ -224,6 +225,36 @@ cudaError_t hist_one(const HistArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// ---- single-tile sort ---------------------------------------------------------------------------------------------
+template <int V, bool F>
+cudaError_t single_one(const SingleArgs& a, cudaStream_t s) {
+  using S = SingleTileShape<K, V>;
+  SingleTileParams<K, F> p;
+  p.keys_in = a.keys_in;
+  p.keys_out = a.keys_out;
+  p.vals_in = a.vals_in;
+  p.vals_out = a.vals_out;
+  p.n = (unsigned int)a.n;
+  p.pad_key = a.dc.pad_key;
+  p.op = make_op<F>(a.dc, a.begin_bit, 8);
+  p.begin_bit = a.begin_bit;
+  p.end_bit = a.end_bit;
+  p.ones = 0xffffffffu;
+  auto kern = single_tile_kernel<K, V, F>;
+  cudaError_t e = ensure_smem(kern, S::TOTAL);
+  if (e != cudaSuccess) return e;
+  kern<<<1, S::NT, S::TOTAL, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int V>
+cudaError_t single_v(const SingleArgs& a, cudaStream_t s) {
+  if constexpr (K >= 2) {
+    if (a.dc.is_float) return single_one<V, true>(a, s);
+  }
+  return single_one<V, false>(a, s);
+}
+
 // ---- multi-GPU partition pass (4- and 8-byte keys; values 0/4/8 bytes) -----------------------
 #if !defined(B2S_TUNING) && (B2S_K == 4 || B2S_K == 8)
 constexpr int SPLIT_NT = 512;
@@ -310,6 +341,27 @@ cudaError_t CAT(onesweep_launch_k, B2S_K)(int variant, const PassArgs& a, cudaSt
 #endif
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t CAT(single_launch_k, B2S_K)(const SingleArgs& a, cudaStream_t s) {
+  switch (a.vbytes) {
+    case 0: return single_v<0>(a, s);
+    case 4: return single_v<4>(a, s);
+    case 8: return single_v<8>(a, s);
+#ifndef B2S_TUNING
+    case 1: return single_v<1>(a, s);
+    case 2: return single_v<2>(a, s);
+    case 16: return single_v<16>(a, s);
+#endif
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+int CAT(single_tile_items_k, B2S_K)(int vbytes) {
+#ifdef B2S_TUNING
+  if (!(vbytes == 0 || vbytes == 4 || vbytes == 8)) return 0;
+#endif
+  return (K + vbytes <= 16) ? SingleTileShape<K, 0>::NT * 16 : SingleTileShape<K, 0>::NT * 8;
 }
 
 Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes, bool is_float) {

@@ -115,6 +115,10 @@ int b2s_timing_read(float *ms, int capacity);
 int b2s_set_variant(int variant);
 int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int *threads, int *items_per_thread,
                          int *min_ctas_per_sm, int *match_mode);
+/* Test hook: sorts of at most one tile (8192 items of up to 16 bytes, 4096 beyond) normally run as ONE kernel that keeps
+ * every digit pass in shared memory (the reference's single-tile path, dispatch_radix_sort.cuh:1272).  0 sends them through the
+ * multi-kernel path instead, so that tests can cover it at small sizes; returns the previous setting.  Also B2S_SINGLE_TILE=0. */
+int b2s_set_single_tile(int enable);
 /* Scheduling mode of a variant: bits 0-1 = 0 one tile per CTA, 1/2 persistent CTAs (next tile claimed after/before the
  * write-out); bits 12+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
 int b2s_variant_mode(int key_bytes, int value_bytes, int variant);

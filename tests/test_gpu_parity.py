@@ -71,6 +71,49 @@ def test_all_key_types_vs_oracle(b2s, oracle, kt):
                              label=f"{H.KEY_NAMES[kt]} n={n} pairs desc={desc}")
 
 
+@pytest.mark.parametrize("kt", [6, 7, 8, 9, 5, 0])
+def test_small_sizes_through_the_multi_kernel_path(b2s, oracle, kt):
+    """Sorts of at most one tile take the single-tile kernel by default (covered by every small case in this file);
+    with the hook off the same sizes must come out of the histogram + digit-pass kernels bit-exactly too."""
+    rng = np.random.default_rng(300 + kt)
+    nb = H.KEY_BYTES[kt]
+    old = b2s.b2s_set_single_tile(0)
+    try:
+        for n in (1, 33, 4097, 8192):
+            raw = H.random_bits(rng, n, nb)
+            if kt in (5, 8):
+                raw = H.spice_floats(raw, nb)
+            _run_and_compare(b2s, oracle, raw, np.arange(n, dtype=np.uint32), kt, n % 2 == 1, label=f"multi-kernel kt={kt} n={n}")
+        assert b2s.b2s_last_launch_count() > 1
+    finally:
+        b2s.b2s_set_single_tile(old)
+
+
+def test_single_tile_kernel_shapes(b2s, oracle):
+    """One launch for a sort of at most one tile: tile boundaries, bit sub-ranges, wide values, selector parity."""
+    rng = np.random.default_rng(77)
+    for kt, vb, n in ((6, 4, 8192), (6, 4, 8191), (9, 16, 4096), (9, 8, 8192), (2, 0, 8192), (0, 1, 5000), (11, 4, 8000)):
+        raw = H.random_bits(rng, n, H.KEY_BYTES[kt])
+        if kt == 11:
+            raw = H.spice_floats(raw, 8)
+        if vb == 16:
+            vals = rng.integers(0, np.iinfo(np.int64).max, size=(n, 2), dtype=np.int64).view(np.uint64)
+        elif vb:
+            vals = H.random_bits(rng, n, vb)
+        else:
+            vals = None
+        for desc in (False, True):
+            _run_and_compare(b2s, oracle, raw, vals, kt, desc, label=f"single tile kt={kt} v={vb} n={n} desc={desc}")
+            assert b2s.b2s_last_launch_count() == 1
+    raw = H.random_bits(rng, 6000, 4)
+    for bb, eb in ((3, 12), (0, 1), (31, 32), (7, 25)):
+        _run_and_compare(b2s, oracle, raw, np.arange(6000, dtype=np.uint32), 6, False, bb, eb, label=f"single tile bits=[{bb},{eb})")
+    # one item more than the tile: the multi-kernel path
+    raw = H.random_bits(rng, 8193, 4)
+    _run_and_compare(b2s, oracle, raw, np.arange(8193, dtype=np.uint32), 6, False, label="8193 items")
+    assert b2s.b2s_last_launch_count() > 1
+
+
 @pytest.mark.parametrize("vbytes", [1, 2, 4, 8, 16])
 @pytest.mark.parametrize("kt", [6, 9, 2, 0])
 def test_value_widths(b2s, oracle, kt, vbytes):
