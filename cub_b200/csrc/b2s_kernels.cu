@@ -43,7 +43,7 @@ constexpr int scale_ipt(int ipt) {
 template <int V, bool F = false>
 constexpr Variant variant_cfg(int vi) {
   // {threads, items/thread, min CTAs/SM, look-back window, -, mode}.  Production points from the B200 sweeps in
-  // profiles/r1_tune_sweep_*.jsonl (last sweeps: tune_r1w, tune_r1x): three 384-thread CTAs per SM; early counts, branch-free
+  // profiles/r1_tune_sweep_*.jsonl (last sweeps: tune_r1w, tune_r1x): three 384-thread CTAs per SM (two 512-thread ones with 22 items for 8-byte integer pairs: +0.8 %); early counts, branch-free
   // look-back window of 12-16 tiles, ballot complements on the FMA pipe, block-index tile ids, L2 prefetch 222 tiles ahead
   // (see MODE in b2s_onesweep.cuh).  56 registers per thread: a variant that spills loses 15-25 %, so floating keys (their
   // transform needs registers) and pairs take fewer items per thread than integer keys alone.
@@ -51,7 +51,7 @@ constexpr Variant variant_cfg(int vi) {
   const bool small_pairs = V > 0 && K + V <= 8;
   const Variant d = V == 0       ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
                     : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
-                    : small_pairs ? Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M}
+                    : (small_pairs && !F) ? Variant{512, scale_ipt<V>(22), 2, 12, 0, M}  // 8-byte pairs: two 11264-pair tiles
                                   : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M};
 #ifdef B2S_TUNING
   switch (vi) {
