@@ -388,3 +388,43 @@ def test_host_sorter_pipeline(oracle, depth):
     for (k, v, _hk, _hv), (gk, gv) in zip(inputs, outputs):
         ek, ev = oracle.radix_sort(k, v, 6)
         assert np.array_equal(gk, ek) and np.array_equal(gv, ev)
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA graphs: a sort is stream-ordered work only (no allocation, no synchronisation), so it can be captured
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [5000, 300_000])
+def test_cuda_graph_capture_and_replay(b2s, oracle, n):
+    """Capture one pointer-form SortPairs (single-tile kernel for n = 5000, memset + histogram + 4 digit passes for
+    n = 300000) in a CUDA graph and replay it on fresh inputs: the replays must sort whatever is in the input buffers."""
+    import cub_b200 as cb
+
+    rng = np.random.default_rng(n)
+    keys = torch.empty(n, dtype=torch.int32, device="cuda")
+    vals = torch.empty(n, dtype=torch.int32, device="cuda")
+    keys_out, vals_out = torch.empty_like(keys), torch.empty_like(vals)
+    err, nbytes = cb.DeviceRadixSort.SortPairs(None, 0, keys, keys_out, vals, vals_out, n)
+    assert err == 0
+    temp = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    raw0 = H.random_bits(rng, n, 4)
+    keys.copy_(H.to_dev(raw0))
+    vals.copy_(H.to_dev(np.arange(n, dtype=np.uint32)))
+    # warm-up outside the capture (first use opts the kernels in to their shared-memory size)
+    err, _ = cb.DeviceRadixSort.SortPairs(temp, nbytes, keys, keys_out, vals, vals_out, n)
+    assert err == 0
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        err, _ = cb.DeviceRadixSort.SortPairs(temp, nbytes, keys, keys_out, vals, vals_out, n)
+    assert err == 0
+    for rep in range(3):
+        raw = H.random_bits(rng, n, 4)
+        v = rng.permutation(n).astype(np.uint32)
+        keys.copy_(H.to_dev(raw))
+        vals.copy_(H.to_dev(v))
+        keys_out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        ek, ev = oracle.radix_sort(raw, v, 7)  # the tensors are int32: signed order
+        assert np.array_equal(H.to_np(keys_out, np.uint32), ek), f"graph replay {rep}: keys differ"
+        assert np.array_equal(H.to_np(vals_out, np.uint32), ev), f"graph replay {rep}: values differ"
