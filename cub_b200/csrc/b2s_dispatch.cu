@@ -208,7 +208,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     sa.begin_bit = begin_bit;
     sa.end_bit = end_bit;
     sa.vbytes = vbytes;
-    g_events_used = 0;
+    if (g_timing) g_events_used = 0;
     timing_mark(stream);
     cudaError_t e1 = ks->single(sa, stream);
     if (e1 != cudaSuccess) return (int)e1;
@@ -224,7 +224,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   unsigned char* status[2] = {base + L.off_status0, base + L.off_status1};
   const size_t osz = off64 ? 8 : 4;
 
-  g_events_used = 0;
+  if (g_timing) g_events_used = 0;  // the timing hook is single-threaded by contract; plain sorts never touch shared state
   timing_mark(stream);
   cudaError_t e = cudaMemsetAsync(base + L.off_ctrs, 0, L.zero_bytes, stream);
   if (e != cudaSuccess) return (int)e;
