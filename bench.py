@@ -349,15 +349,20 @@ def run_ours(a):
     # e2e: host shards in, host shards out
     h_keys = keys.view(torch.int32).cpu().pin_memory()
     h_vals = vals.view(torch.int32).cpu().pin_memory()
+    e2e_steps = max(1, min(a.steps, 3))
+    # pinned result buffers of the sorter's receive capacity (shard sizes are data dependent); device input buffers reused
+    hk_out = torch.empty(sorter.capacity, dtype=torch.int32).pin_memory()
+    hv_out = torch.empty(sorter.capacity, dtype=torch.int32).pin_memory()
+    dk = torch.empty(n, dtype=torch.int32, device="cuda")
+    dv = torch.empty(n, dtype=torch.int32, device="cuda")
     barrier()
     e0.record()
-    e2e_steps = max(1, min(a.steps, 3))
     for _ in range(e2e_steps):
-        dk = h_keys.to("cuda", non_blocking=True).view(torch.uint32)
-        dv = h_vals.to("cuda", non_blocking=True).view(torch.uint32)
-        o = sorter.sort(dk, dv)
-        hk = o.keys.view(torch.int32).to("cpu", non_blocking=True)
-        hv = o.values.view(torch.int32).to("cpu", non_blocking=True)
+        dk.copy_(h_keys, non_blocking=True)
+        dv.copy_(h_vals, non_blocking=True)
+        o = sorter.sort(dk.view(torch.uint32), dv.view(torch.uint32))
+        hk_out[:o.count].copy_(o.keys.view(torch.int32)[:o.count], non_blocking=True)
+        hv_out[:o.count].copy_(o.values.view(torch.int32)[:o.count], non_blocking=True)
     e1.record()
     barrier()
     e2e = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device="cuda")
