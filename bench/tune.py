@@ -18,7 +18,7 @@ from cub_b200 import _lib  # noqa: E402
 from tests import harness as H  # noqa: E402
 
 CASES = {"k4v4": (6, 4, 1), "k4v0": (6, 0, 1), "k8v4": (9, 4, 1), "k8v0": (9, 0, 1), "k4v8": (6, 8, 1),
-         "k2v0": (2, 0, 1), "k8v4and3": (9, 4, 3), "k1v0": (0, 0, 1), "k2v4": (2, 4, 1)}
+         "k2v0": (2, 0, 1), "k8v8": (9, 8, 1), "k8v4and3": (9, 4, 3), "k1v0": (0, 0, 1), "k2v4": (2, 4, 1)}
 
 
 def time_sort(fn_db, keys, vals, kt, iters=5, warm=2, bb=0, eb=None):
