@@ -25,7 +25,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 29;
+constexpr int NUM_VARIANTS = 31;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -90,6 +90,9 @@ constexpr Variant variant_cfg(int vi) {
     case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16 | 512};
     case 27: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 16 | d.mode};          // production, time stamps only
     case 28: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 16 | 512 | d.mode};    // + look-back statistics (spills)
+    // round-2 candidates, written but not measured yet: chunked key copy (bit 10)
+    case 29: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 1024 | d.mode};
+    case 30: return Variant{384, scale_ipt<V>(V == 0 ? 24 : 20), 3, 12, 0, 1024 | M};
     default: return d;
   }
 #else

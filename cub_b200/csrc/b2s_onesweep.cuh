@@ -80,6 +80,8 @@ struct OnesweepSmem {
 //       bit 4 = (tuning) thread 0 records the SM clock at every phase boundary into P.trace;
 //       bit 8 = branch-free look-back window (all LBW words summed with a select chain when every one is published);
 //       bit 9 = (tuning, with bit 4) look-back statistics in trace slots 11-14;
+//       bit 10 = (experiment, not measured yet) the key copy is issued as four chunks (one per quarter of the warps) with
+//                their own mbarriers, so that a warp's counting sweep starts as soon as ITS keys have landed;
 //       bits 12+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
 template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0,
           int MODE = 0>
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   // the ranking loop.
   constexpr bool EARLY = (MODE & 128) != 0;
   constexpr bool FASTLB = (MODE & 256) != 0;
+  constexpr bool CHUNKED = (MODE & 1024) != 0 && (NT / 32) % 4 == 0 && (NT / 128 * 32 * IPT * KBYTES) % 16 == 0;
+  static_assert(!((MODE & 1024) && PERSIST), "chunked key copies are for one-tile CTAs");
   static_assert(!(BLOCKID && PERSIST), "persistent CTAs claim their tiles");
   static_assert(!(EARLY && ABL), "ablations apply to the classic flow");
   // stamps go to shared memory (fixed address, no registers held) and are copied out once per tile
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_MISC);            // [2]
   unsigned int* s_wtot = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 16);  // [8]
   unsigned int* s_tile = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 64);
+  uint64_t* kbar = reinterpret_cast<uint64_t*>(smem + L::OFF_MISC + 80);       // [4], CHUNKED only
 
   int tid = threadIdx.x;
   B2S_TRACE(11);  // CTA entry
@@ -134,6 +139,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
     if (!BLOCKID) *s_tile = atomicAdd(P.tile_counter, 1u);
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    if (CHUNKED) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) mbar_init(&kbar[g], 1);
+    }
     mbar_fence_init();
   }
   if (!BLOCKID) {
@@ -195,8 +204,17 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   if (bulk) {
     if (tid == 0) {
       if (PERSIST && (MODE & 4)) fence_proxy_async();  // (experiment) cross-proxy fence before re-filling the buffers
-      mbar_expect_tx(&bar[0], kbytes);
-      bulk_g2s(stage_k, reinterpret_cast<const void*>(kaddr - kshift), kbytes, &bar[0]);
+      if (CHUNKED && kshift == 0) {
+        constexpr unsigned int CH = NT / 128 * 32 * IPT * KBYTES;  // the keys of a quarter of the warps
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          mbar_expect_tx(&kbar[g], CH);
+          bulk_g2s(stage_k + g * CH, reinterpret_cast<const void*>(kaddr + g * CH), CH, &kbar[g]);
+        }
+      } else {
+        mbar_expect_tx(&bar[0], kbytes);
+        bulk_g2s(stage_k, reinterpret_cast<const void*>(kaddr - kshift), kbytes, &bar[0]);
+      }
       if (HAS_VALUES) {
         mbar_expect_tx(&bar[1], vbytes);
         bulk_g2s(stage_v, reinterpret_cast<const void*>(vaddr - vshift), vbytes, &bar[1]);
@@ -227,7 +245,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   W key[IPT];
   unsigned int rk[IPT];  // (digit << 16) | rank inside this warp's digit bucket
   {
-    if (bulk) mbar_wait(&bar[0], phase);
+    if (bulk) {
+      if (CHUNKED && kshift == 0) mbar_wait(&kbar[warp / (NW / 4)], phase);
+      else mbar_wait(&bar[0], phase);
+    }
     B2S_TRACE(2);  // keys staged
     const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + kshift);
 #pragma unroll
