@@ -23,6 +23,10 @@
  *   - pointer form never writes keys_in / values_in;
  *   - DoubleBuffer form may clobber both buffers and updates the selectors so
  *     that bufs[selector] holds the result.
+ * What a call enqueues: 1 memset + 1 histogram kernel + one digit-pass kernel per 8 key bits; for at most one tile
+ * (8192 items of up to 16 bytes, 4096 beyond) ONE single-CTA kernel that needs no temp storage (the size query and
+ * the "too small" check stay the same, as in the reference's single-tile path, dispatch_radix_sort.cuh:1272).  Only
+ * stream-ordered work with arguments fixed at call time: a call can be captured into a CUDA graph and replayed.
  *
  * No torch types, no C++ types: plain pointers and sizes only.
  */
