@@ -25,7 +25,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 31;
+constexpr int NUM_VARIANTS = 34;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -93,6 +93,10 @@ constexpr Variant variant_cfg(int vi) {
     // round-2 candidates, written but not measured yet: chunked key copy (bit 10)
     case 29: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 1024 | d.mode};
     case 30: return Variant{384, scale_ipt<V>(V == 0 ? 24 : 20), 3, 12, 0, 1024 | M};
+    // early first look-back window (bit 11), alone and with the chunked copy
+    case 31: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 2048 | d.mode};
+    case 32: return Variant{d.nt, d.ipt, d.minb, 8, 0, 2048 | d.mode};
+    case 33: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 2048 | 1024 | d.mode};
     default: return d;
   }
 #else

@@ -82,6 +82,8 @@ struct OnesweepSmem {
 //       bit 9 = (tuning, with bit 4) look-back statistics in trace slots 11-14;
 //       bit 10 = (experiment, not measured yet) the key copy is issued as four chunks (one per quarter of the warps) with
 //                their own mbarriers, so that a warp's counting sweep starts as soon as ITS keys have landed;
+//       bit 11 = (experiment, not measured yet) the first look-back window is requested four rows before the end of the
+//                ranking sweep -- the key registers that have died by then hold it -- so that its L2 round trip is hidden;
 //       bits 12+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
 template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0,
           int MODE = 0>
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   // the ranking loop.
   constexpr bool EARLY = (MODE & 128) != 0;
   constexpr bool FASTLB = (MODE & 256) != 0;
+  constexpr bool EARLYWIN = (MODE & 2048) != 0 && EARLY && FASTLB && IPT > 6;
   constexpr bool CHUNKED = (MODE & 1024) != 0 && (NT / 32) % 4 == 0 && (NT / 128 * 32 * IPT * KBYTES) % 16 == 0;
   static_assert(!((MODE & 1024) && PERSIST), "chunked key copies are for one-tile CTAs");
   static_assert(!(BLOCKID && PERSIST), "persistent CTAs claim their tiles");
@@ -337,6 +340,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   __syncthreads();  // S3: per-warp bases ready
   B2S_TRACE(4);  // digit scan done
 
+  // EARLYWIN: first look-back window, requested from inside the ranking sweep
+  OffT win0[EARLYWIN ? LBW : 1];
+  const bool pre_window = EARLYWIN && tid < RADIX && tile >= (unsigned long long)LBW;
+
   // ---- P3: reorder keys in shared memory (staged keys were all consumed before S2)
   if (EARLY) {
     // ranking sweep on counters that hold absolute tile positions: the leader's atomic returns the position of the first
@@ -359,6 +366,10 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
         const unsigned int r = bcast_prev + below_prev;
         rk[u - 1] = r;
         sk[r] = (KeyU)key[u - 1];
+      }
+      if (EARLYWIN && u == IPT - 4) {
+        if (pre_window)
+          load_status_window<RADIX * (int)sizeof(OffT)>(status - RADIX + tid, win0, std::make_integer_sequence<int, LBW>{});
       }
       bcast_prev = __shfl_sync(0xffffffffu, raw, leader);
       below_prev = below;
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       const OffT* p = status - RADIX + tid;  // first entry of the current window
       unsigned long long left = tile;        // predecessors not yet examined
       bool done = false;
+      bool have_window = pre_window;  // EARLYWIN: the first window is already on its way (or here)
       unsigned int n_trips = 0, n_spins = 0, n_walked = 0;  // TRACE only
       long long t_first = 0;
       while (true) {
@@ -409,7 +421,13 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
           // common case: the whole window exists and every word in it is published.  An inclusive word carries BOTH flag
           // bits, so "all published" is one AND-reduction; the sum up to the nearest inclusive word is a select chain
           // from the far end (no branches, no loads with computed addresses)
-          load_status_window<RADIX * (int)sizeof(OffT)>(p, win, std::make_integer_sequence<int, LBW>{});
+          if (EARLYWIN && have_window) {
+#pragma unroll
+            for (int j = 0; j < LBW; ++j) win[j] = win0[j];
+          } else {
+            load_status_window<RADIX * (int)sizeof(OffT)>(p, win, std::make_integer_sequence<int, LBW>{});
+          }
+          have_window = false;
           OffT all = win[0], any = win[0];
 #pragma unroll
           for (int j = 1; j < LBW; ++j) {
