@@ -59,6 +59,7 @@ struct DigitOp {
   uint32_t bit;  // first bit of this pass' digit
   uint32_t mask; // (1 << digit_bits) - 1
 
+  static constexpr int kMaxDigit = 255;  // largest value operator() can return
   static constexpr int KBITS = KBYTES * 8;
   static constexpr int WBITS = sizeof(W) * 8;
   static constexpr W ONES = KBYTES == 8 ? ~W(0) : (W)((1ull << (KBITS % 64)) - 1);
@@ -90,6 +91,7 @@ struct SplitterOp {
   using W = typename WideOf<KBYTES>::type;
   using KeyU = typename UIntOf<KBYTES>::type;
   static constexpr int MAX_SPLITTERS = 7;
+  static constexpr int kMaxDigit = MAX_SPLITTERS;  // destinations 0 .. count
   DigitOp<KBYTES, IS_FLOAT> base;  // .bit = begin_bit of the sort; .mask unused
   W range_mask;                    // ones over (end_bit - begin_bit) bits
   const void* d_keys;              // DEVICE: `count` raw splitter keys, ascending in sort order

@@ -77,7 +77,7 @@ struct Variant {
   int nt, ipt, minb;
   int lbw;  // look-back window (predecessor tiles read per round trip)
   int abl;  // tuning builds only: timing ablation switches (0 in every product variant)
-  int mode; // bits 0-1: 0 one tile per CTA, 1/2 persistent CTAs (late/early tile claim); bits 8+: L2 prefetch distance (tiles)
+  int mode; // flag bits 0-15 as documented at onesweep_kernel (b2s_onesweep.cuh); bits 16+: L2 prefetch distance (tiles)
 };
 
 // Implemented once per key width in b2s_kernels.cu (-DB2S_K=1|2|4|8)

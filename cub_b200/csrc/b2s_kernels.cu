@@ -47,7 +47,7 @@ constexpr Variant variant_cfg(int vi) {
   // look-back window of 12-16 tiles, ballot complements on the FMA pipe, block-index tile ids, L2 prefetch 222 tiles ahead
   // (see MODE in b2s_onesweep.cuh).  56 registers per thread: a variant that spills loses 15-25 %, so floating keys (their
   // transform needs registers) and pairs take fewer items per thread than integer keys alone.
-  constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 12);
+  constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);
   const bool small_pairs = V > 0 && K + V <= 8;
   const Variant d = V == 0       ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
                     : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
@@ -68,11 +68,11 @@ constexpr Variant variant_cfg(int vi) {
     case 8: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 2, 0};
     case 9: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 8, 0};
     // the ladder from variant 3 to production, one technique at a time (MODE bits in b2s_onesweep.cuh)
-    case 10: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 222 << 12};                            // + L2 prefetch
-    case 11: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | (222 << 12)};                      // + IMAD complement
-    case 12: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 256 | (222 << 12)};          // + branch-free window of 12
-    case 13: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 128 | 256 | (222 << 12)};    // + early counts
-    case 14: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 32 | 64 | 128 | 256 | (222 << 12)};  // + block-index tile ids
+    case 10: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 222 << 16};                            // + L2 prefetch
+    case 11: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | (222 << 16)};                      // + IMAD complement
+    case 12: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 256 | (222 << 16)};          // + branch-free window of 12
+    case 13: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 128 | 256 | (222 << 16)};    // + early counts
+    case 14: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 32 | 64 | 128 | 256 | (222 << 16)};  // + block-index tile ids
     // neighbours of the production point
     case 15: return Variant{384, scale_ipt<V>(20), 3, 8, 0, M};
     case 16: return Variant{384, scale_ipt<V>(20), 3, 16, 0, M};
@@ -84,7 +84,7 @@ constexpr Variant variant_cfg(int vi) {
     // rejected: persistent CTAs (the tile loop makes the ranking sweep spill), serial wide window, unfenced early claim
     case 22: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1};
     case 23: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2};
-    case 24: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 64 | (148 << 12)};
+    case 24: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 64 | (148 << 16)};
     // phase-timestamp traces (bench/trace.py): old production, classic 384, production
     case 25: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 512};
     case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16 | 512};
@@ -289,7 +289,13 @@ cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
   constexpr int IPT = split_ipt<V>();
   using L = OnesweepSmem<K, V, SPLIT_NT, IPT>;
   using Op = SplitterOp<K, F>;
-  auto kern = onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER>;
+  // B2S_SPLIT_WIDE=1 selects the per-run 16-byte-store write-out (MODE bit 12; written in round 1, not measured yet)
+  static const bool wide = [] {
+    const char* e = std::getenv("B2S_SPLIT_WIDE");
+    return e && e[0] == '1';
+  }();
+  auto kern = wide ? onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER, 0, 4096>
+                   : onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER>;
   cudaError_t e = ensure_smem(kern, L::TOTAL);
   if (e != cudaSuccess) return e;
   OnesweepParams<K, Op> p;

@@ -71,6 +71,31 @@ struct OnesweepSmem {
   static constexpr int TOTAL = OFF_MISC + 256;  // barriers, scan partials, tile id; +128: phase stamps of the trace variants
 };
 
+// One run of the sorted tile -> its destination, cooperatively by the CTA: single items up to the destination's first
+// 16-byte boundary and after its last one, 16-byte stores in between (the shared-memory source has no such alignment: it
+// is read item by item).
+template <typename T>
+__device__ __forceinline__ void copy_run_wide(T* dst, const T* src, int len, int tid, int nt) {
+  constexpr int A = 16 / (int)sizeof(T);
+  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte items");
+  int head = (int)(((16u - (unsigned int)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) / sizeof(T));
+  if (head > len) head = len;
+  const int groups = (len - head) / A;
+  const int tail_at = head + groups * A;
+  if (tid < head) dst[tid] = src[tid];
+  if (tid < len - tail_at) dst[tail_at + tid] = src[tail_at + tid];
+  for (int g = tid; g < groups; g += nt) {
+    const T* s = src + head + g * A;
+    union {
+      uint4 v;
+      T t[A];
+    } u;
+#pragma unroll
+    for (int i = 0; i < A; ++i) u.t[i] = s[i];
+    *reinterpret_cast<uint4*>(dst + head + g * A) = u.v;
+  }
+}
+
 // ABL: timing-only ablation switches for bench/tune.py (results are WRONG when non-zero; never used by the product):
 //   1 = no global stores in P4, 2 = no P4 at all, 4 = no ranking sweep, 8 = no look-back walk, 16 = no P3/P4 value path
 // MODE: bits 0-1 = 0 one tile per CTA (grid = tiles) | 1 persistent CTA (grid = resident CTAs), next tile claimed after the
@@ -84,7 +109,8 @@ struct OnesweepSmem {
 //                their own mbarriers, so that a warp's counting sweep starts as soon as ITS keys have landed;
 //       bit 11 = (experiment, not measured yet) the first look-back window is requested four rows before the end of the
 //                ranking sweep -- the key registers that have died by then hold it -- so that its L2 round trip is hidden;
-//       bits 12+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
+//       bit 12 = (experiment, not measured yet; splitter passes only) write-out per destination run with 16-byte stores;
+//       bits 16+ = L2 prefetch distance in tiles (the CTA of tile t asks L2 for the keys/values of tile t + distance).
 template <int KBYTES, int VBYTES, typename OpT, typename OffT, int NT, int IPT, int MINB, int LBW, bool PEER, int ABL = 0,
           int MODE = 0>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams<KBYTES, OpT> P) {
@@ -100,6 +126,9 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   constexpr bool EARLY = (MODE & 128) != 0;
   constexpr bool FASTLB = (MODE & 256) != 0;
   constexpr bool EARLYWIN = (MODE & 2048) != 0 && EARLY && FASTLB && IPT > 6;
+  constexpr bool WIDE = (MODE & 4096) != 0;  // few long runs (<= MAX_PEERS destinations): 16-byte stores per run
+  static_assert(!WIDE || (OpT::kMaxDigit < MAX_PEERS && !EARLY && (KBYTES == 4 || KBYTES == 8) && (VBYTES == 0 || VBYTES == 4 || VBYTES == 8)),
+                "wide write-out is for the splitter pass of the classic flow");
   constexpr bool CHUNKED = (MODE & 1024) != 0 && (NT / 32) % 4 == 0 && (NT / 128 * 32 * IPT * KBYTES) % 16 == 0;
   static_assert(!((MODE & 1024) && PERSIST), "chunked key copies are for one-tile CTAs");
   static_assert(!(BLOCKID && PERSIST), "persistent CTAs claim their tiles");
@@ -109,7 +138,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
   do {                                                                                                       \
     if (TRACE && threadIdx.x == 0) reinterpret_cast<long long*>(smem + L::OFF_MISC + 128)[slot] = clock64(); \
   } while (0)
-  constexpr int PFD = MODE >> 12;
+  constexpr int PFD = MODE >> 16;
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
   using ValU = typename UIntOf<VBYTES ? VBYTES : 1>::type;
@@ -519,7 +548,30 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const OnesweepParams
       if (HAS_VALUES) ovals[(ABL & 4) ? dst % (OffT)P.n : dst] = sv[pos];
     };
     if (ABL & 2) return;
-    if (full) {
+    if constexpr (WIDE) {
+      // Splitter pass: at most MAX_PEERS runs of ~TILE / (ranks) items each.  Per run: the items up to the first
+      // 16-byte boundary of the destination and after the last one go out singly, the middle as 16-byte stores (one warp
+      // instruction covers 512 contiguous bytes of the destination -- full-size NVLink packets for the remote runs).
+      // In the classic flow warp 0's counter row still holds every digit's first position in the sorted tile.
+#pragma unroll 1
+      for (int d = 0; d < MAX_PEERS; ++d) {
+        const int s0 = (int)whist[d];
+        int s1 = d + 1 < MAX_PEERS ? (int)whist[d + 1] : TILE;
+        if (s1 > valid) s1 = valid;
+        if (s1 <= s0) continue;
+        const OffT g0 = s_goff[d] + (OffT)s0;
+        long long len = s1 - s0;
+        if (PEER) {
+          if ((unsigned long long)g0 >= P.peer_capacity) continue;
+          const unsigned long long room = P.peer_capacity - (unsigned long long)g0;
+          if ((unsigned long long)len > room) len = (long long)room;
+          okeys = reinterpret_cast<KeyU*>(P.peer_keys[d]);
+          ovals = reinterpret_cast<ValU*>(P.peer_vals[d]);
+        }
+        copy_run_wide(okeys + g0, sk + s0, (int)len, tid, NT);
+        if constexpr (HAS_VALUES) copy_run_wide(ovals + g0, sv + s0, (int)len, tid, NT);
+      }
+    } else if (full) {
 #pragma unroll
       for (int u = 0; u < IPT; ++u) emit(u * NT + tid);
     } else {

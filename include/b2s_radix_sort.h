@@ -124,7 +124,7 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int *threa
  * multi-kernel path instead, so that tests can cover it at small sizes; returns the previous setting.  Also B2S_SINGLE_TILE=0. */
 int b2s_set_single_tile(int enable);
 /* Scheduling mode of a variant: bits 0-1 = 0 one tile per CTA, 1/2 persistent CTAs (next tile claimed after/before the
- * write-out); bits 12+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
+ * write-out); bits 16+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
 int b2s_variant_mode(int key_bytes, int value_bytes, int variant);
 /* Tuning builds: digit pass number `pass` of every following sort writes per-tile phase timestamps (u64[tiles][16], SM clock
  * cycles; slot 0 = global timer in ns, slot 15 = SM id) to d_trace when the active variant is a trace variant.  NULL disables. */
