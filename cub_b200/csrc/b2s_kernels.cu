@@ -25,7 +25,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 34;
+constexpr int NUM_VARIANTS = 38;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -97,6 +97,11 @@ constexpr Variant variant_cfg(int vi) {
     case 31: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 2048 | d.mode};
     case 32: return Variant{d.nt, d.ipt, d.minb, 8, 0, 2048 | d.mode};
     case 33: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 2048 | 1024 | d.mode};
+    // keys alone: larger tiles (pairs run out of shared memory / registers here: time these on keys-only cases)
+    case 34: return Variant{384, scale_ipt<V>(26), 3, 12, 0, M};
+    case 35: return Variant{384, scale_ipt<V>(28), 3, 12, 0, M};
+    case 36: return Variant{384, scale_ipt<V>(30), 3, 12, 0, M};
+    case 37: return Variant{384, scale_ipt<V>(28), 3, 12, 0, 2048 | 1024 | M};
     default: return d;
   }
 #else
