@@ -25,7 +25,7 @@ constexpr int K = B2S_K;
 // points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
 // with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 38;
+constexpr int NUM_VARIANTS = 40;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -102,6 +102,8 @@ constexpr Variant variant_cfg(int vi) {
     case 35: return Variant{384, scale_ipt<V>(28), 3, 12, 0, M};
     case 36: return Variant{384, scale_ipt<V>(30), 3, 12, 0, M};
     case 37: return Variant{384, scale_ipt<V>(28), 3, 12, 0, 2048 | 1024 | M};
+    case 38: return Variant{512, scale_ipt<V>(28), 2, 12, 0, M};
+    case 39: return Variant{512, scale_ipt<V>(32), 2, 12, 0, M};
     default: return d;
   }
 #else
