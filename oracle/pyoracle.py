@@ -22,6 +22,7 @@ TK_LIB = os.path.join(_HERE, "_ref", "libtk_cub.so")
 # b2s_key_t order (include/b2s_radix_sort.h); numpy view dtype of the raw bits
 KEY_NAMES = ["u8", "i8", "u16", "i16", "f16", "bf16", "u32", "i32", "f32", "u64", "i64", "f64"]
 KEY_BYTES = [1, 1, 2, 2, 2, 2, 4, 4, 4, 8, 8, 8]
+KEY_CATEGORY = [0, 1, 0, 1, 2, 2, 0, 1, 2, 0, 1, 2]  # 0 unsigned, 1 signed, 2 floating (b2s_key_t order)
 BITS_DTYPE = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
 
 _cpu = None
@@ -127,3 +128,53 @@ def load_gpu_reference(which: str = "ref"):
     lib.sort = getattr(lib, prefix + "_radix_sort")
     lib.sort_db = getattr(lib, prefix + "_radix_sort_db")
     return lib
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Decomposer (custom struct key) semantics -- checker for SURVEY.md §8(f)2, no product counterpart yet.
+# Reference: the decomposer overloads of cub::DeviceRadixSort (cub/device/device_radix_sort.cuh:486-530, 625-666, ...):
+# a key is a tuple of arithmetic fields; the sort key is the concatenation of the fields' bit-ordered images, first tuple
+# element most significant, LAST element holding bit 0 (test/catch2_test_device_radix_sort_custom.cu:1100-1115);
+# [begin_bit, end_bit) indexes that concatenation; every field is transformed like a fundamental key (util_type.cuh:1031,
+# 1078, 1179), -0.0 compares equal to +0.0 in a floating field (radix_rank_sort_operations.cuh:79-89), descending inverts
+# the whole image (:592-599); the sort is stable.
+# ---------------------------------------------------------------------------------------------------------------------
+def _ordered_field(bits: np.ndarray, key_type: int) -> np.ndarray:
+    """Bit-ordered image of one field as uint64 (only the low 8*bytes bits are used)."""
+    nbits = KEY_BYTES[key_type] * 8
+    ones = (1 << nbits) - 1
+    high = 1 << (nbits - 1)
+    k = bits.astype(np.uint64)
+    cat = KEY_CATEGORY[key_type]
+    if cat == 0:
+        return k
+    if cat == 1:
+        return k ^ np.uint64(high)
+    neg_zero = k == np.uint64(high)
+    k = np.where(neg_zero, np.uint64(0), k)  # -0.0 orders (and is digit-extracted) as +0.0
+    sign = (k >> np.uint64(nbits - 1)) & np.uint64(1)
+    return k ^ np.where(sign == 1, np.uint64(ones), np.uint64(high))
+
+
+def decomposed_sort_permutation(fields, descending=False, begin_bit=0, end_bit=None):
+    """fields: list of (raw bits array, key_type), most significant first.  Returns the stable permutation `perm` such that
+    records[perm] is the sorted sequence over bits [begin_bit, end_bit) of the concatenated image."""
+    widths = [KEY_BYTES[kt] * 8 for _, kt in fields]
+    total = sum(widths)
+    if end_bit is None:
+        end_bit = total
+    keys = []
+    lo = 0  # bit offset of the current field inside the concatenation, starting from the LAST field
+    for (bits, kt), w in zip(reversed(fields), reversed(widths)):
+        img = _ordered_field(np.ascontiguousarray(bits), kt)
+        if descending:
+            img = img ^ np.uint64((1 << w) - 1)
+        b, e = max(begin_bit, lo), min(end_bit, lo + w)
+        if e > b:
+            mask = ((1 << (e - lo)) - 1) ^ ((1 << (b - lo)) - 1)
+            keys.append(img & np.uint64(mask))
+        else:
+            keys.append(np.zeros_like(img))
+        lo += w
+    # np.lexsort: last key is the primary one and the sort is stable; `keys` runs from least to most significant field
+    return np.lexsort(tuple(keys))
