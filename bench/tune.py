@@ -117,7 +117,7 @@ def main():
                 ok = bool(torch.equal(ko, golden[0]) and (vo is None or torch.equal(vo, golden[1])))
             rec = {"case": case, "n": n, "impl": "b2s", "variant": v, "nt": nt.value, "ipt": ipt.value,
                    "minb": minb.value, "match": match.value, "mode": b2s.b2s_variant_mode(kbytes, vbytes, v) & 3,
-                   "pfd": b2s.b2s_variant_mode(kbytes, vbytes, v) >> 16, "modeflags": b2s.b2s_variant_mode(kbytes, vbytes, v) & 65535, "best_ms": best, "median_ms": med,
+                   "flow": b2s.b2s_variant_flow(kbytes, vbytes, v), "pfd": b2s.b2s_variant_mode(kbytes, vbytes, v) >> 16, "modeflags": b2s.b2s_variant_mode(kbytes, vbytes, v) & 65535, "best_ms": best, "median_ms": med,
                    "gkeys_s": n / best / 1e6, "algo_gbs": algo_bytes / best / 1e6, "bit_exact_vs_ref": ok}
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")

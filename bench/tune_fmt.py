@@ -9,5 +9,5 @@ for l in sys.stdin:
     kind = lbw = None
     if m is not None:
         kind, lbw, m = m >> 16, (m >> 8) & 255, m & 15
-    print(r.get("case"), r.get("impl"), "v", r.get("variant"), r.get("nt"), r.get("ipt"), r.get("minb"), "abl", kind, "lbw", lbw, "mode", r.get("modeflags", r.get("mode")), "pfd", r.get("pfd"),
+    print(r.get("case"), r.get("impl"), "v", r.get("variant"), r.get("nt"), r.get("ipt"), r.get("minb"), "abl", kind, "lbw", lbw, "flow", r.get("flow"),
           round(r["gkeys_s"], 2), "GK/s", round(r["best_ms"], 3), "ms", r.get("bit_exact_vs_ref"))

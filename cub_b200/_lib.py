@@ -38,6 +38,8 @@ EXPORTS = {
     "b2s_set_variant": (_c.c_int, [_c.c_int]),
     "b2s_describe_variant": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int] + [_c.POINTER(_c.c_int)] * 4),
     "b2s_variant_mode": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int]),
+    "b2s_variant_flow": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int]),
+    "b2s_set_tile_claim": (_c.c_int, [_c.c_int]),
     "b2s_set_trace": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "b2s_set_single_tile": (_c.c_int, [_c.c_int]),
     "b2s_enable_peer_access": (_c.c_int, [_c.c_int]),

@@ -76,6 +76,18 @@ bool g_single_tile = [] {
   const char* e = std::getenv("B2S_SINGLE_TILE");
   return !(e && e[0] == '0');
 }();
+// Tile ids of the digit pass: block index (default; CTAs are dispatched in index order, the assumption CUB's decoupled
+// look-back scan makes too) or an atomic ticket taken by every CTA (B2S_TILE_CLAIM=1 / b2s_set_tile_claim(1)): with
+// tickets a tile's predecessors are always running or finished whatever the dispatch order, at ~1.5 % of throughput.
+// B2S_SPLIT_BULK=0 keeps the partition pass on item stores (A/B runs of the multi-GPU exchange)
+bool g_split_bulk = [] {
+  const char* e = std::getenv("B2S_SPLIT_BULK");
+  return !(e && e[0] == '0');
+}();
+bool g_claim = [] {
+  const char* e = std::getenv("B2S_TILE_CLAIM");
+  return e && e[0] == '1';
+}();
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;
@@ -83,9 +95,9 @@ int g_trace_pass = -1;
 struct KernelSet {
   cudaError_t (*hist)(const HistArgs&, cudaStream_t);
   cudaError_t (*onesweep)(int, const PassArgs&, cudaStream_t);
-  int (*tile)(int, int, bool);
+  int (*tile)(int, int, bool, bool);
   int (*num_variants)();
-  Variant (*variant)(int, int, bool);
+  Variant (*variant)(int, int, bool, bool);
   cudaError_t (*split_count)(const SplitArgs&, cudaStream_t);
   cudaError_t (*split)(const SplitArgs&, cudaStream_t);
   int (*split_tile)(int);
@@ -181,9 +193,9 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   const KernelSet* ks = kernels_for(kbytes);
   int variant = tuning_variant();
   if (variant < 0 || variant >= ks->num_variants()) variant = 0;
-  const int tile = ks->tile(variant, vbytes, ki.category == 2);
   const int passes = (num_bits + 7) / 8;
   const bool off64 = n >= (1ull << 30);
+  const int tile = ks->tile(variant, vbytes, ki.category == 2, off64);
   const bool need_alt = !overwrite && passes > 1;
   const Layout L = carve(n, kbytes, vbytes, passes, tile, off64, need_alt);
 
@@ -288,6 +300,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     a.off64 = off64;
     a.vbytes = vbytes;
     a.trace = (g_trace_pass == p) ? g_trace : nullptr;
+    a.claim = g_claim;
     e = ks->onesweep(variant, a, stream);
     if (e != cudaSuccess) return (int)e;
     g_last_launches++;
@@ -428,12 +441,16 @@ int b2s_split_scatter(void* d_temp_storage, size_t* temp_storage_bytes, const vo
   a.pass.tile_counter = reinterpret_cast<unsigned int*>(base + L.off_ctr);
   a.peer = peer_keys != nullptr;
   a.peer_capacity = peer_capacity;
+  uintptr_t align_or = reinterpret_cast<uintptr_t>(d_keys_out) | reinterpret_cast<uintptr_t>(d_values_out);
   if (a.peer) {
+    align_or = 0;
     for (int d = 0; d <= num_splitters; ++d) {
       a.peer_keys[d] = peer_keys[d];
       a.peer_vals[d] = (value_bytes && peer_vals) ? peer_vals[d] : nullptr;
+      align_or |= reinterpret_cast<uintptr_t>(a.peer_keys[d]) | reinterpret_cast<uintptr_t>(a.peer_vals[d]);
     }
   }
+  a.bulk = (align_or & 15) == 0 && b2s::g_split_bulk;
   return (int)ks->split(a, s);
 }
 
@@ -504,7 +521,7 @@ int b2s_set_variant(int variant) {
 int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, int* ipt, int* minb, int* match) {
   const b2s::KernelSet* ks = b2s::kernels_for(key_bytes);
   if (!ks || variant < 0 || variant >= ks->num_variants()) return -1;
-  const b2s::Variant v = ks->variant(variant, value_bytes, false);
+  const b2s::Variant v = ks->variant(variant, value_bytes, false, false);
   if (nt) *nt = v.nt;
   if (ipt) *ipt = v.ipt;
   if (minb) *minb = v.minb;
@@ -524,10 +541,22 @@ int b2s_set_trace(void* d_trace, int pass) {
   return 0;
 }
 
+int b2s_set_tile_claim(int enable) {
+  const int old = b2s::g_claim ? 1 : 0;
+  b2s::g_claim = enable != 0;
+  return old;
+}
+
+int b2s_variant_flow(int key_bytes, int value_bytes, int variant) {
+  const b2s::KernelSet* ks = b2s::kernels_for(key_bytes);
+  if (!ks || variant < 0 || variant >= ks->num_variants()) return -2;
+  return ks->variant(variant, value_bytes, false, false).flow;
+}
+
 int b2s_variant_mode(int key_bytes, int value_bytes, int variant) {
   const b2s::KernelSet* ks = b2s::kernels_for(key_bytes);
   if (!ks || variant < 0 || variant >= ks->num_variants()) return -1;
-  return ks->variant(variant, value_bytes, false).mode;
+  return ks->variant(variant, value_bytes, false, false).mode;
 }
 
 }  // extern "C"

@@ -42,6 +42,7 @@ struct PassArgs {
   bool off64;
   int vbytes;
   unsigned long long* trace;  // tuning builds: per-tile phase timestamps (u64[tiles][16]) of one selected pass, else null
+  bool claim;                 // tile ids from an atomic ticket instead of the block index (see b2s_set_tile_claim)
 };
 
 // Whole sort of one small tile in a single launch (b2s_single_tile.cuh).
@@ -68,6 +69,7 @@ struct SplitArgs {
   void* peer_keys[8];                // non-null => write destination d into peer_keys[d] / peer_vals[d]
   void* peer_vals[8];
   bool peer;
+  bool bulk;                         // every destination base is 16-byte aligned: runs leave the SM as bulk copies
   uint64_t peer_capacity;            // items per peer receive buffer
   uint64_t* counts;                  // count launch: uint64[num_splitters + 1], zeroed by the caller
 };
@@ -77,16 +79,17 @@ struct Variant {
   int nt, ipt, minb;
   int lbw;  // look-back window (predecessor tiles read per round trip)
   int abl;  // tuning builds only: timing ablation switches (0 in every product variant)
-  int mode; // flag bits 0-15 as documented at onesweep_kernel (b2s_onesweep.cuh); bits 16+: L2 prefetch distance (tiles)
+  int mode; // laboratory kernel only: flag bits 0-15 as documented at onesweep_kernel (b2s_onesweep.cuh); bits 16+: L2 prefetch distance (tiles)
+  int flow; // >= 0: production kernel (b2s_pass.cuh) with these PF_* flags; < 0: laboratory kernel (tuning builds)
 };
 
 // Implemented once per key width in b2s_kernels.cu (-DB2S_K=1|2|4|8)
 #define B2S_DECL_K(K)                                                                         \
   cudaError_t hist_launch_k##K(const HistArgs& a, cudaStream_t s);                            \
   cudaError_t onesweep_launch_k##K(int variant, const PassArgs& a, cudaStream_t s);           \
-  int onesweep_tile_k##K(int variant, int vbytes, bool is_float);                             \
+  int onesweep_tile_k##K(int variant, int vbytes, bool is_float, bool off64);                          \
   int onesweep_num_variants_k##K();                                                           \
-  Variant onesweep_variant_k##K(int variant, int vbytes, bool is_float);                      \
+  Variant onesweep_variant_k##K(int variant, int vbytes, bool is_float, bool off64);                   \
   cudaError_t split_count_launch_k##K(const SplitArgs& a, cudaStream_t s);                    \
   cudaError_t split_launch_k##K(const SplitArgs& a, cudaStream_t s);                          \
   int split_tile_k##K(int vbytes);                                                            \

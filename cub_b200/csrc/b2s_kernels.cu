@@ -7,7 +7,10 @@
 
 #include "b2s_histogram.cuh"
 #include "b2s_internal.h"
-#include "b2s_onesweep.cuh"
+#include "b2s_pass.cuh"
+#ifdef B2S_TUNING
+#include "b2s_onesweep.cuh"  // laboratory kernel: tuning library only
+#endif
 #include "b2s_single_tile.cuh"
 #include "b2s_split.cuh"
 
@@ -21,9 +24,10 @@ namespace {
 constexpr int K = B2S_K;
 
 // ---- tuning table -------------------------------------------------------------------------
-// Variant 0 is the production tuning for (K, V).  A tuning build (-DB2S_TUNING) adds more
-// points that bench/tune.py sweeps on the GPU.  Table entries give items/thread for 4-byte keys
-// with <=4-byte values; wider items scale it down by bytes (shared memory) and by registers.
+// Variant 0 is the production tuning for (K, V).  A tuning build (-DB2S_TUNING) adds more points that bench/tune.py
+// sweeps on the GPU: 1..29 = other shapes / flows of the production kernel (b2s_pass.cuh), 30.. = the round-1
+// laboratory kernel (b2s_onesweep.cuh).  Table entries give items/thread for 4-byte keys with <=4-byte values; wider
+// items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
 constexpr int NUM_VARIANTS = 40;
 #else
@@ -33,77 +37,78 @@ constexpr int NUM_VARIANTS = 1;
 template <int V>
 constexpr int scale_ipt(int ipt) {
   const int kw = K > 4 ? 2 : 1, vw = (V + 3) / 4;
-  const int regs_per_item = (vw > kw ? vw : kw) + 1;  // key words (values re-use them) + packed rank
+  const int regs_per_item = (vw > kw ? vw : kw) + 1;  // key words (values re-use them) + slot
   const int by_bytes = (K + V <= 8) ? ipt : ipt * 8 / (K + V);
   const int by_regs = ipt * 2 / regs_per_item;
   const int r = by_bytes < by_regs ? by_bytes : by_regs;
   return r < 4 ? 4 : r;
 }
 
-template <int V, bool F = false>
+// Fewer items per thread when the TMA write-out pads every digit run (b2s_pass.cuh PassSmem): SLOTS * (K + V) bytes.
+template <int V>
+constexpr int tmaw_ipt(int nt, int minb, int want) {
+  int ipt = want;
+  while (ipt > 4) {
+    const int a = 16 / ((V && V < K) ? V : K);
+    const long slots = (long)nt * ipt + 256 * (2 * a - 2);
+    const long bytes = slots * (K + V) + 256 + (nt / 32) * 1024 + 2048 + 1024 + 128 + 1024;
+    if (bytes * minb <= 232448 && slots < 65536) break;
+    --ipt;
+  }
+  return ipt;
+}
+
+template <int V, bool F = false, bool OFF64 = false>
 constexpr Variant variant_cfg(int vi) {
-  // {threads, items/thread, min CTAs/SM, look-back window, -, mode}.  Production points from the B200 sweeps in
-  // profiles/r1_tune_sweep_*.jsonl (last sweeps: tune_r1w, tune_r1x): three 384-thread CTAs per SM (two 512-thread ones with 22 items for 8-byte integer pairs: +0.8 %); early counts, branch-free
-  // look-back window of 12-16 tiles, ballot complements on the FMA pipe, block-index tile ids, L2 prefetch 222 tiles ahead
-  // (see MODE in b2s_onesweep.cuh).  56 registers per thread: a variant that spills loses 15-25 %, so floating keys (their
-  // transform needs registers) and pairs take fewer items per thread than integer keys alone.
-  constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);
+  // {threads, items/thread, min CTAs/SM, look-back window, -, lab mode, flow}.  flow >= 0: production kernel with these
+  // PF_* flags; flow < 0: laboratory kernel with `mode` (tuning builds).  Shapes from the B200 sweeps in
+  // profiles/r1_tune_sweep_*.jsonl and profiles/r2_*.jsonl.  A variant that spills loses 15-25 %, so floating keys
+  // (their transform needs registers) and pairs take fewer items per thread than integer keys alone.
   const bool small_pairs = V > 0 && K + V <= 8;
-  const Variant d = V == 0       ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
-                    : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, M}
-                    : (small_pairs && !F) ? Variant{512, scale_ipt<V>(22), 2, 12, 0, M}  // 8-byte pairs: two 11264-pair tiles
-                                  : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, M};
+  const bool pair44 = K == 4 && V == 4;
+  const Variant d = V == 0                  ? Variant{384, scale_ipt<V>(F ? 22 : (K <= 4 ? 26 : 24)), 3, 12, 0, 0, 0}
+                    : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, 0, 0}
+                    : pair44                ? Variant{448, (F ? 22 : 24) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR}  // (key, value) as one 64-bit store
+                    : (small_pairs && !F)   ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0}
+                                            : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, 0, 0};
 #ifdef B2S_TUNING
+  constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);  // lab kernel: the round-1 production flow
   switch (vi) {
     case 0: return d;
-    // the kernel as it stood at the start of this series (classic flow: ranking produces the counts, serial LBW=4 walk)
-    case 1: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 0};
-    case 2: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 0};
-    case 3: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 0};
-    // timing-only ablations of variant 1 (wrong results by design): see ABL in b2s_onesweep.cuh
-    case 4: return Variant{512, scale_ipt<V>(20), 2, 4, 1, 0};
-    case 5: return Variant{512, scale_ipt<V>(20), 2, 4, 2, 0};
-    case 6: return Variant{512, scale_ipt<V>(20), 2, 4, 4, 0};
-    case 7: return Variant{512, scale_ipt<V>(20), 2, 4, 8, 0};
-    case 8: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 2, 0};
-    case 9: return Variant{512, scale_ipt<V>(20), 2, 4, 4 | 8, 0};
-    // the ladder from variant 3 to production, one technique at a time (MODE bits in b2s_onesweep.cuh)
-    case 10: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 222 << 16};                            // + L2 prefetch
-    case 11: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 8 | (222 << 16)};                      // + IMAD complement
-    case 12: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 256 | (222 << 16)};          // + branch-free window of 12
-    case 13: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 128 | 256 | (222 << 16)};    // + early counts
-    case 14: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 32 | 64 | 128 | 256 | (222 << 16)};  // + block-index tile ids
-    // neighbours of the production point
-    case 15: return Variant{384, scale_ipt<V>(20), 3, 8, 0, M};
-    case 16: return Variant{384, scale_ipt<V>(20), 3, 16, 0, M};
-    case 17: return Variant{384, scale_ipt<V>(22), 3, 12, 0, M};
-    case 18: return Variant{384, scale_ipt<V>(24), 3, 12, 0, M};
-    case 19: return Variant{512, scale_ipt<V>(22), 2, 12, 0, M};
-    case 20: return Variant{512, scale_ipt<V>(20), 2, 12, 0, M};
-    case 21: return Variant{256, scale_ipt<V>(20), 4, 8, 0, M};
-    // rejected: persistent CTAs (the tile loop makes the ranking sweep spill), serial wide window, unfenced early claim
-    case 22: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 1};
-    case 23: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 2};
-    case 24: return Variant{256, scale_ipt<V>(20), 4, 16, 0, 8 | 64 | (148 << 16)};
-    // phase-timestamp traces (bench/trace.py): old production, classic 384, production
-    case 25: return Variant{256, scale_ipt<V>(20), 4, 4, 0, 16 | 512};
-    case 26: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 16 | 512};
-    case 27: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 16 | d.mode};          // production, time stamps only
-    case 28: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 16 | 512 | d.mode};    // + look-back statistics (spills)
-    // round-2 candidates, written but not measured yet: chunked key copy (bit 10)
-    case 29: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 1024 | d.mode};
-    case 30: return Variant{384, scale_ipt<V>(V == 0 ? 24 : 20), 3, 12, 0, 1024 | M};
-    // early first look-back window (bit 11), alone and with the chunked copy
-    case 31: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 2048 | d.mode};
-    case 32: return Variant{d.nt, d.ipt, d.minb, 8, 0, 2048 | d.mode};
-    case 33: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 2048 | 1024 | d.mode};
-    // keys alone: larger tiles (pairs run out of shared memory / registers here: time these on keys-only cases)
-    case 34: return Variant{384, scale_ipt<V>(26), 3, 12, 0, M};
-    case 35: return Variant{384, scale_ipt<V>(28), 3, 12, 0, M};
-    case 36: return Variant{384, scale_ipt<V>(30), 3, 12, 0, M};
-    case 37: return Variant{384, scale_ipt<V>(28), 3, 12, 0, 2048 | 1024 | M};
-    case 38: return Variant{512, scale_ipt<V>(28), 2, 12, 0, M};
-    case 39: return Variant{512, scale_ipt<V>(32), 2, 12, 0, M};
+    // production kernel, split flow at the round-1 production shapes (A/B against the lab kernel, variant 30)
+    case 1: return small_pairs && !F ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0} : Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 0, 0};
+    case 2: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 0, d.flow | PF_CLAIM};  // ticketed tile ids
+    // pair flow shapes
+    case 3: return Variant{512, scale_ipt<V>(20), 2, 12, 0, 0, PF_PAIR};
+    case 4: return Variant{448, scale_ipt<V>(22), 2, 12, 0, 0, PF_PAIR};
+    case 5: return Variant{384, scale_ipt<V>(26), 2, 12, 0, 0, PF_PAIR};
+    case 6: return Variant{448, scale_ipt<V>(24), 2, 8, 0, 0, PF_PAIR};
+    // TMA write-out (bulk shared->global copies per digit run)
+    case 7: return Variant{512, tmaw_ipt<V>(512, 2, scale_ipt<V>(22)), 2, 12, 0, 0, PF_TMAW};
+    case 8: return Variant{384, tmaw_ipt<V>(384, 3, scale_ipt<V>(20)), 3, 12, 0, 0, PF_TMAW};
+    case 9: return Variant{448, tmaw_ipt<V>(448, 2, scale_ipt<V>(24)), 2, 12, 0, 0, PF_TMAW};
+    case 10: return Variant{512, tmaw_ipt<V>(512, 2, scale_ipt<V>(22)), 2, 6, 0, 0, PF_TMAW};
+    case 11: return Variant{1024, tmaw_ipt<V>(1024, 1, scale_ipt<V>(22)), 1, 12, 0, 0, PF_TMAW};
+    case 12: return Variant{256, tmaw_ipt<V>(256, 4, scale_ipt<V>(22)), 4, 12, 0, 0, PF_TMAW};
+    // keys alone / other shapes of the split flow
+    case 13: return Variant{384, scale_ipt<V>(24), 3, 12, 0, 0, 0};
+    case 14: return Variant{384, scale_ipt<V>(26), 3, 12, 0, 0, 0};
+    case 15: return Variant{384, scale_ipt<V>(22), 3, 12, 0, 0, 0};
+    case 16: return Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0};
+    case 17: return Variant{256, scale_ipt<V>(26), 4, 12, 0, 0, 0};
+    // laboratory kernel (round 1): production flow, classic flow, the ladder, traces
+    case 30: return small_pairs && !F ? Variant{512, scale_ipt<V>(22), 2, 12, 0, M, -1}
+                                      : Variant{384, scale_ipt<V>(V == 0 ? (F ? 22 : 24) : (K + V <= 6 && V >= 2) ? (F ? 22 : 24) : (F ? 18 : 20)), 3, 12, 0, M, -1};
+    case 31: return Variant{512, scale_ipt<V>(20), 2, 4, 0, 0, -1};                                   // classic flow
+    case 32: return Variant{384, scale_ipt<V>(19), 3, 4, 0, 0, -1};
+    case 33: return Variant{384, scale_ipt<V>(19), 3, 12, 0, 8 | 64 | 128 | 256 | (222 << 16), -1};   // early counts, claimed ids
+    case 34: return Variant{512, scale_ipt<V>(22), 2, 12, 0, 16 | M, -1};                             // phase time stamps
+    case 35: return Variant{512, scale_ipt<V>(22), 2, 12, 0, 16 | 512 | M, -1};                       // + look-back statistics
+    // timing-only ablations of the classic flow (wrong results by design): see ABL in b2s_onesweep.cuh
+    case 36: return Variant{512, scale_ipt<V>(20), 2, 4, 1, 0, -1};
+    case 37: return Variant{512, scale_ipt<V>(20), 2, 4, 2, 0, -1};
+    case 38: return Variant{512, scale_ipt<V>(20), 2, 4, 4, 0, -1};
+    case 39: return Variant{512, scale_ipt<V>(20), 2, 4, 8, 0, -1};
     default: return d;
   }
 #else
@@ -174,21 +179,43 @@ void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
 
 template <int V, bool F, typename OffT, int VI>
 cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
-  constexpr Variant c = variant_cfg<V, F>(VI);
+  constexpr Variant c = variant_cfg<V, F, sizeof(OffT) == 8>(VI);
   constexpr int TILE = c.nt * c.ipt;
-  using L = OnesweepSmem<K, V, c.nt, c.ipt>;
   OnesweepParams<K, DigitOp<K, F>> p;
   fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
   const unsigned long long tiles = (a.n + TILE - 1) / TILE;
   // 64-bit look-back words cost two registers each: half the window
   constexpr int LBW = (sizeof(OffT) == 8 && c.lbw > 4) ? c.lbw / 2 : c.lbw;
-  auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, false, c.abl, c.mode>;
-  cudaError_t e = ensure_smem(kern, L::TOTAL);
-  if (e != cudaSuccess) return e;
-  unsigned long long grid = tiles;
-  if ((c.mode & 3) && grid > (unsigned long long)resident_ctas(c.minb)) grid = resident_ctas(c.minb);
-  kern<<<(unsigned int)grid, c.nt, L::TOTAL, s>>>(p);
-  return cudaGetLastError();
+#ifdef B2S_TUNING
+  if constexpr (c.flow < 0) {
+    using L = OnesweepSmem<K, V, c.nt, c.ipt>;
+    auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, false, c.abl, c.mode>;
+    cudaError_t e = ensure_smem(kern, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    unsigned long long grid = tiles;
+    if ((c.mode & 3) && grid > (unsigned long long)resident_ctas(c.minb)) grid = resident_ctas(c.minb);
+    kern<<<(unsigned int)grid, c.nt, L::TOTAL, s>>>(p);
+    return cudaGetLastError();
+  } else
+#endif
+  {
+    constexpr int FL = c.flow < 0 ? 0 : c.flow;
+    constexpr bool TMAW = (FL & PF_TMAW) != 0 && !((FL & PF_PAIR) && K == 4 && V == 4) && K >= 4 && (V == 0 || V == 4 || V == 8);
+    using L = PassSmem<K, V, c.nt, c.ipt, TMAW>;
+    auto launch = [&](auto kern) {
+      cudaError_t e = ensure_smem(kern, L::TOTAL);
+      if (e != cudaSuccess) return e;
+      kern<<<(unsigned int)tiles, c.nt, L::TOTAL, s>>>(p);
+      return cudaGetLastError();
+    };
+#ifdef B2S_TUNING
+    return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL>);
+#else
+    // ticketed tile ids on request (b2s_set_tile_claim / B2S_TILE_CLAIM=1): no reliance on in-order CTA dispatch
+    if (a.claim) return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL | PF_CLAIM>);
+    return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL>);
+#endif
+  }
 }
 
 template <int V, bool F, typename OffT, int... VI>
@@ -270,10 +297,10 @@ cudaError_t single_v(const SingleArgs& a, cudaStream_t s) {
 }
 
 // ---- multi-GPU partition pass (4- and 8-byte keys; values 0/4/8 bytes) -----------------------
-#if !defined(B2S_TUNING) && (B2S_K == 4 || B2S_K == 8)
+#if (B2S_K == 4 || B2S_K == 8)
 constexpr int SPLIT_NT = 512;
 template <int V>
-constexpr int split_ipt() { return scale_ipt<V>(16); }  // the destination functor is register-hungry
+constexpr int split_ipt() { return tmaw_ipt<V>(SPLIT_NT, 2, scale_ipt<V>(16)); }  // the destination functor is register-hungry
 
 template <bool F>
 SplitterOp<K, F> make_splitter_op(const SplitArgs& a) {
@@ -294,17 +321,7 @@ SplitterOp<K, F> make_splitter_op(const SplitArgs& a) {
 template <int V, bool F, bool PEER>
 cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
   constexpr int IPT = split_ipt<V>();
-  using L = OnesweepSmem<K, V, SPLIT_NT, IPT>;
   using Op = SplitterOp<K, F>;
-  // B2S_SPLIT_WIDE=1 selects the per-run 16-byte-store write-out (MODE bit 12; written in round 1, not measured yet)
-  static const bool wide = [] {
-    const char* e = std::getenv("B2S_SPLIT_WIDE");
-    return e && e[0] == '1';
-  }();
-  auto kern = wide ? onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER, 0, 4096>
-                   : onesweep_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 4, PEER>;
-  cudaError_t e = ensure_smem(kern, L::TOTAL);
-  if (e != cudaSuccess) return e;
   OnesweepParams<K, Op> p;
   fill_params(p, a.pass, make_splitter_op<F>(a));
   for (int i = 0; i < MAX_PEERS; ++i) {
@@ -312,8 +329,23 @@ cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
     p.peer_vals[i] = a.peer_vals[i];
   }
   p.peer_capacity = a.peer_capacity;
-  const unsigned long long tiles = (a.pass.n + L::TILE - 1) / L::TILE;
-  kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
+  const unsigned long long tiles = (a.pass.n + SPLIT_NT * IPT - 1) / (SPLIT_NT * IPT);
+  constexpr int BASE = PEER ? PF_PEER : 0;
+  // With <= 8 destinations the runs of a tile are ~1000 items long: every run leaves the SM as one bulk shared->global
+  // (or shared->peer over NVLink) copy when the destinations are 16-byte aligned (`bulk`); item stores otherwise.
+  if (a.bulk) {
+    using L = PassSmem<K, V, SPLIT_NT, IPT, true>;
+    auto kern = digit_pass_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 6, BASE | PF_TMAW>;
+    cudaError_t e = ensure_smem(kern, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
+  } else {
+    using L = PassSmem<K, V, SPLIT_NT, IPT, false>;
+    auto kern = digit_pass_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 6, BASE>;
+    cudaError_t e = ensure_smem(kern, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
+  }
   return cudaGetLastError();
 }
 
@@ -384,8 +416,11 @@ int CAT(single_tile_items_k, B2S_K)(int vbytes) {
   return (K + vbytes <= 16) ? SingleTileShape<K, 0>::NT * 16 : SingleTileShape<K, 0>::NT * 8;
 }
 
-Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes, bool is_float) {
-#define B2S_VCASE(V) case V: return is_float ? variant_cfg<V, true>(variant) : variant_cfg<V, false>(variant);
+Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes, bool is_float, bool off64) {
+#define B2S_VCASE(V)                                                                                           \
+  case V:                                                                                                      \
+    return is_float ? (off64 ? variant_cfg<V, true, true>(variant) : variant_cfg<V, true, false>(variant))     \
+                    : (off64 ? variant_cfg<V, false, true>(variant) : variant_cfg<V, false, false>(variant));
   switch (vbytes) {
     B2S_VCASE(0)
     B2S_VCASE(1)
@@ -393,19 +428,19 @@ Variant CAT(onesweep_variant_k, B2S_K)(int variant, int vbytes, bool is_float) {
     B2S_VCASE(4)
     B2S_VCASE(8)
     B2S_VCASE(16)
-    default: return Variant{0, 0, 0, 0, 0};
+    default: return Variant{0, 0, 0, 0, 0, 0, 0};
   }
 #undef B2S_VCASE
 }
 
-int CAT(onesweep_tile_k, B2S_K)(int variant, int vbytes, bool is_float) {
-  const Variant v = CAT(onesweep_variant_k, B2S_K)(variant, vbytes, is_float);
+int CAT(onesweep_tile_k, B2S_K)(int variant, int vbytes, bool is_float, bool off64) {
+  const Variant v = CAT(onesweep_variant_k, B2S_K)(variant, vbytes, is_float, off64);
   return v.nt * v.ipt;
 }
 
 int CAT(onesweep_num_variants_k, B2S_K)() { return NUM_VARIANTS; }
 
-#if !defined(B2S_TUNING) && (B2S_K == 4 || B2S_K == 8)
+#if (B2S_K == 4 || B2S_K == 8)
 cudaError_t CAT(split_count_launch_k, B2S_K)(const SplitArgs& a, cudaStream_t s) {
   return a.pass.dc.is_float ? split_count_one<true>(a, s) : split_count_one<false>(a, s);
 }

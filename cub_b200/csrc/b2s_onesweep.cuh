@@ -1,4 +1,7 @@
-// b2s_onesweep.cuh -- one digit pass of the LSD sort: stable partition of all n items by one
+// b2s_onesweep.cuh -- LABORATORY version of the digit pass (tuning library only, -DB2S_TUNING; the product kernel is
+// digit_pass_kernel in b2s_pass.cuh): the round-1 kernel with its ablation / trace / persistent / experiment branches,
+// kept for A/B runs and the phase traces of bench/trace.py.
+// One digit pass of the LSD sort: stable partition of all n items by one
 // 8-bit digit into their global positions, chained-scan ("onesweep") style.
 //
 // Replaces (reference, for parity of RESULT only):
@@ -29,33 +32,9 @@
 // tiles are ordered by their id == position in the input.
 #pragma once
 #include "b2s_common.cuh"
+#include "b2s_pass.cuh"  // OnesweepParams, MAX_PEERS, look-back helpers shared with the production kernel
 
 namespace b2s {
-
-constexpr int MAX_PEERS = 8;
-
-template <int KBYTES, typename OpT>
-struct OnesweepParams {
-  const void* keys_in;
-  void* keys_out;
-  const void* vals_in;
-  void* vals_out;
-  void* status;        // OffT[num_tiles][256], zero on entry
-  void* status_next;   // OffT[num_tiles][256] cleared here for the next pass (may be null)
-  const void* bins;    // OffT[256] exclusive digit offsets of this pass
-  unsigned int* tile_counter;
-  unsigned long long n;
-  unsigned long long pad_key;  // raw key whose bit-ordered form is all ones
-  unsigned long long* trace;   // tuning builds, MODE bit 4: u64[tiles][16] phase timestamps (null otherwise)
-  unsigned int ones;           // 0xffffffff, as a launch parameter so that the compiler cannot fold it (see agree_bit)
-  OpT op;              // key -> digit of this pass (DigitOp), or key -> destination rank (SplitterOp)
-  // PEER launches only (multi-GPU exchange fused into the partition pass): digit d is written to
-  // peer_keys[d] / peer_vals[d] -- receive buffers of rank d mapped into this process -- instead of keys_out.
-  void* peer_keys[MAX_PEERS];
-  void* peer_vals[MAX_PEERS];
-  unsigned long long peer_capacity;  // items per receive buffer: stores at or beyond it are dropped (the host detects
-                                     // the overflow from the count matrix afterwards; nothing is ever corrupted)
-};
 
 template <int KBYTES, int VBYTES, int NT, int IPT>
 struct OnesweepSmem {

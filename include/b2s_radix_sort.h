@@ -126,6 +126,14 @@ int b2s_set_single_tile(int enable);
 /* Scheduling mode of a variant: bits 0-1 = 0 one tile per CTA, 1/2 persistent CTAs (next tile claimed after/before the
  * write-out); bits 16+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
 int b2s_variant_mode(int key_bytes, int value_bytes, int variant);
+/* Kernel and flow of a variant: >= 0 production kernel (b2s_pass.cuh) with these flag bits (1 = (key,value) scattered as
+ * one 64-bit store, 2 = bulk-copy write-out, 4 = ticketed tile ids); -1 laboratory kernel (tuning builds); -2 unknown. */
+int b2s_variant_flow(int key_bytes, int value_bytes, int variant);
+/* Tile ids of the digit pass.  0 (default): tile id = block index -- relies on CTAs being dispatched in index order, as
+ * CUB's decoupled look-back scan does (cub/agent/agent_scan.cuh).  1: every CTA takes an atomic ticket, as the reference's
+ * onesweep agent does (cub/agent/agent_radix_sort_onesweep.cuh:650-687): forward progress of the look-back then holds
+ * under ANY dispatch order, at ~1.5 % of throughput.  Also B2S_TILE_CLAIM=1.  Returns the previous setting. */
+int b2s_set_tile_claim(int enable);
 /* Tuning builds: digit pass number `pass` of every following sort writes per-tile phase timestamps (u64[tiles][16], SM clock
  * cycles; slot 0 = global timer in ns, slot 15 = SM id) to d_trace when the active variant is a trace variant.  NULL disables. */
 int b2s_set_trace(void *d_trace, int pass);

@@ -42,8 +42,10 @@ def test_sass_is_sm100a_with_bulk_copy():
     assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
     syms = subprocess.run(["cuobjdump", "-symbols", _lib.LIB_PATH], capture_output=True, text=True).stdout
     names = sorted({t for line in syms.splitlines() for t in line.split()
-                    if "onesweep_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEj" in t and not t.startswith("$")})
+                    if "digit_pass_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEj" in t and not t.startswith("$")})
     assert names, "production u32/u32 digit-pass kernel not found in libb2s.so"
+    lab = [t for line in syms.splitlines() for t in line.split() if "onesweep_kernel" in t]
+    assert not lab, "the laboratory kernel (ablation / trace branches) must not be in the product library"
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", names[0], _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass, "digit pass must stage its tile with the TMA engine"
     assert "VOTE" in sass and "ATOMS" in sass
