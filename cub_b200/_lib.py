@@ -30,6 +30,18 @@ _SORT_DB_ARGS = [
 EXPORTS = {
     "b2s_radix_sort": (_c.c_int, _SORT_ARGS),
     "b2s_radix_sort_db": (_c.c_int, _SORT_DB_ARGS),
+    "b2s_radix_sort_struct": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_size_t), _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                         _c.c_uint64, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                         _c.c_void_p]),
+    "b2s_radix_sort_struct_db": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_size_t), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int),
+                                            _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _c.c_uint64, _c.c_int, _c.c_void_p,
+                                            _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "b2s_segmented_radix_sort": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_size_t), _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                            _c.c_uint64, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                            _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "b2s_segmented_radix_sort_db": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_size_t), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int),
+                                               _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _c.c_uint64, _c.c_uint64, _c.c_void_p,
+                                               _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "b2s_key_bytes": (_c.c_int, [_c.c_int]),
     "b2s_version": (_c.c_char_p, []),
     "b2s_last_launch_count": (_c.c_int, []),
@@ -38,6 +50,19 @@ EXPORTS = {
     "b2s_set_variant": (_c.c_int, [_c.c_int]),
     "b2s_describe_variant": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int] + [_c.POINTER(_c.c_int)] * 4),
     "b2s_variant_mode": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int]),
+    "b2s_digit_histogram": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                       _c.c_void_p]),
+    "b2s_check_stable": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                    _c.c_void_p, _c.c_void_p]),
+    "b2s_mgpu_unique_id": (_c.c_int, [_c.c_void_p]),
+    "b2s_mgpu_create": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_int, _c.c_int, _c.c_uint64, _c.c_int, _c.c_int,
+                                   _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_int]),
+    "b2s_mgpu_sort": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.POINTER(_c.c_void_p),
+                                 _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.c_void_p]),
+    "b2s_mgpu_last_phases": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_float), _c.POINTER(_c.c_uint64)]),
+    "b2s_mgpu_capacity": (_c.c_uint64, [_c.c_void_p]),
+    "b2s_mgpu_last_error": (_c.c_char_p, [_c.c_void_p]),
+    "b2s_mgpu_destroy": (_c.c_int, [_c.c_void_p]),
     "b2s_variant_flow": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int]),
     "b2s_set_tile_claim": (_c.c_int, [_c.c_int]),
     "b2s_set_trace": (_c.c_int, [_c.c_void_p, _c.c_int]),

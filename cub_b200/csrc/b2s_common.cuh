@@ -123,6 +123,13 @@ struct SplitterOp {
       if (j < count) d += (o > s[j] || (o == s[j] && ((tie >> j) & 1u))) ? 1u : 0u;
     return d;
   }
+  // ge[j] += "k orders at or after splitter j" (the summands of operator()); monotone in j
+  __device__ __forceinline__ void add_ge(W k, uint32_t (&ge)[MAX_SPLITTERS]) const {
+    const W o = sort_key(k);
+#pragma unroll
+    for (int j = 0; j < MAX_SPLITTERS; ++j)
+      if (j < count) ge[j] += (o > s[j] || (o == s[j] && ((tie >> j) & 1u))) ? 1u : 0u;
+  }
 };
 
 // Host-side description of a key type, resolved once per call.

@@ -103,16 +103,17 @@ struct KernelSet {
   int (*split_tile)(int);
   cudaError_t (*single)(const SingleArgs&, cudaStream_t);
   int (*single_items)(int);
+  cudaError_t (*segmented)(const SegmentedArgs&, cudaStream_t);
 };
 const KernelSet* kernels_for(int kbytes) {
   static const KernelSet k1{hist_launch_k1, onesweep_launch_k1, onesweep_tile_k1, onesweep_num_variants_k1, onesweep_variant_k1,
-                            split_count_launch_k1, split_launch_k1, split_tile_k1, single_launch_k1, single_tile_items_k1};
+                            split_count_launch_k1, split_launch_k1, split_tile_k1, single_launch_k1, single_tile_items_k1, segmented_launch_k1};
   static const KernelSet k2{hist_launch_k2, onesweep_launch_k2, onesweep_tile_k2, onesweep_num_variants_k2, onesweep_variant_k2,
-                            split_count_launch_k2, split_launch_k2, split_tile_k2, single_launch_k2, single_tile_items_k2};
+                            split_count_launch_k2, split_launch_k2, split_tile_k2, single_launch_k2, single_tile_items_k2, segmented_launch_k2};
   static const KernelSet k4{hist_launch_k4, onesweep_launch_k4, onesweep_tile_k4, onesweep_num_variants_k4, onesweep_variant_k4,
-                            split_count_launch_k4, split_launch_k4, split_tile_k4, single_launch_k4, single_tile_items_k4};
+                            split_count_launch_k4, split_launch_k4, split_tile_k4, single_launch_k4, single_tile_items_k4, segmented_launch_k4};
   static const KernelSet k8{hist_launch_k8, onesweep_launch_k8, onesweep_tile_k8, onesweep_num_variants_k8, onesweep_variant_k8,
-                            split_count_launch_k8, split_launch_k8, split_tile_k8, single_launch_k8, single_tile_items_k8};
+                            split_count_launch_k8, split_launch_k8, split_tile_k8, single_launch_k8, single_tile_items_k8, segmented_launch_k8};
   switch (kbytes) {
     case 1: return &k1;
     case 2: return &k2;
@@ -314,6 +315,66 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
 }
 
 
+// ---- segmented sort (cub::DeviceSegmentedRadixSort) -----------------------------------------------------------------
+//   overwrite == false: pointer form (kin -> kout; kin never written; an alternate buffer in the temp storage when there is
+//                       more than one pass);  overwrite == true: DoubleBuffer form (selector = parity of the pass count,
+//                       dispatch_radix_sort.cuh:2343-2349)
+int segmented_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], int* selector_out, bool overwrite, uint64_t n,
+                   uint64_t num_segments, const void* begin_offsets, const void* end_offsets, int offset_bytes, int key_type,
+                   int vbytes, bool descending, int begin_bit, int end_bit, cudaStream_t stream) {
+  if (!temp_bytes) return (int)cudaErrorInvalidValue;
+  if (key_type < 0 || key_type >= B2S_KEY_TYPE_COUNT) return (int)cudaErrorInvalidValue;
+  if (!(vbytes == 0 || vbytes == 1 || vbytes == 2 || vbytes == 4 || vbytes == 8 || vbytes == 16)) return (int)cudaErrorInvalidValue;
+  if (!(offset_bytes == 4 || offset_bytes == 8)) return (int)cudaErrorInvalidValue;
+  const KeyInfo ki = kKeyInfo[key_type];
+  const int num_bits = end_bit - begin_bit;
+  if (selector_out) *selector_out = 0;
+  // dispatch_radix_sort.cuh:2369: empty problem, or no bits to sort with double buffering
+  if (n == 0 || num_segments == 0 || (num_bits <= 0 && overwrite)) {
+    if (!d_temp) *temp_bytes = 1;
+    return (int)cudaSuccess;
+  }
+  const int passes = num_bits <= 0 ? 1 : (num_bits + 7) / 8;  // a zero-bit pass copies every segment (:2307)
+  const bool need_alt = !overwrite && passes > 1;
+  size_t o = 0;
+  const size_t off_keys = o;  o += need_alt ? align_up((size_t)n * ki.bytes, 256) : 0;
+  const size_t off_vals = o;  o += (need_alt && vbytes) ? align_up((size_t)n * vbytes, 256) : 0;
+  const size_t total = o + 256;
+  if (!d_temp) {
+    *temp_bytes = total;
+    return (int)cudaSuccess;
+  }
+  if (*temp_bytes < total) return (int)cudaErrorInvalidValue;
+  unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(d_temp), 256));
+  SegmentedArgs a{};
+  a.keys_src = kbuf[0];
+  a.vals_src = vbytes ? vbuf[0] : nullptr;
+  if (overwrite) {
+    const int fin = passes & 1;  // pass p writes buffer (p + 1) & 1: the last one lands in buffer passes & 1
+    a.keys_a = kbuf[fin];
+    a.keys_b = kbuf[fin ^ 1];
+    a.vals_a = vbytes ? vbuf[fin] : nullptr;
+    a.vals_b = vbytes ? vbuf[fin ^ 1] : nullptr;
+    if (selector_out) *selector_out = fin;
+  } else {
+    a.keys_a = kbuf[1];
+    a.keys_b = need_alt ? base + off_keys : nullptr;
+    a.vals_a = vbytes ? vbuf[1] : nullptr;
+    a.vals_b = (need_alt && vbytes) ? base + off_vals : nullptr;
+  }
+  a.begin_offsets = begin_offsets;
+  a.end_offsets = end_offsets;
+  a.offset_bytes = offset_bytes;
+  a.num_segments = num_segments;
+  a.dc = make_consts(ki, descending);
+  a.begin_bit = begin_bit;
+  a.end_bit = end_bit;
+  a.passes = passes;
+  a.vbytes = vbytes;
+  g_last_launches = 1;
+  return (int)kernels_for(ki.bytes)->segmented(a, stream);
+}
+
 // ---- multi-GPU partition pass ---------------------------------------------------------------------------------
 bool fill_split_args(SplitArgs& a, uint64_t n, int key_type, int vbytes, bool descending, int begin_bit, int end_bit,
                      const void* d_splitter_keys, const int* d_splitter_ranks, int num_splitters, int my_rank) {
@@ -482,6 +543,64 @@ int b2s_radix_sort_db(void* d_temp_storage, size_t* temp_storage_bytes, void* ke
     if (value_bytes) *val_selector = vs ^ flipped;
   }
   return r;
+}
+
+int b2s_segmented_radix_sort(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, void* d_keys_out,
+                             const void* d_values_in, void* d_values_out, uint64_t num_items, uint64_t num_segments,
+                             const void* d_begin_offsets, const void* d_end_offsets, int offset_bytes, int key_type,
+                             int value_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream) {
+  void* k[2] = {const_cast<void*>(d_keys_in), d_keys_out};
+  void* v[2] = {const_cast<void*>(d_values_in), d_values_out};
+  return b2s::segmented_impl(d_temp_storage, temp_storage_bytes, k, v, nullptr, false, num_items, num_segments, d_begin_offsets,
+                             d_end_offsets, offset_bytes, key_type, value_bytes, descending != 0, begin_bit, end_bit,
+                             (cudaStream_t)stream);
+}
+
+int b2s_segmented_radix_sort_db(void* d_temp_storage, size_t* temp_storage_bytes, void* key_bufs[2], int* key_selector,
+                                void* val_bufs[2], int* val_selector, uint64_t num_items, uint64_t num_segments,
+                                const void* d_begin_offsets, const void* d_end_offsets, int offset_bytes, int key_type,
+                                int value_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream) {
+  if (!key_bufs || !key_selector) return (int)cudaErrorInvalidValue;
+  if (value_bytes && (!val_bufs || !val_selector)) return (int)cudaErrorInvalidValue;
+  const int ks = *key_selector & 1;
+  const int vs = value_bytes ? (*val_selector & 1) : 0;
+  void* k[2] = {key_bufs[ks], key_bufs[ks ^ 1]};
+  void* v[2] = {value_bytes ? val_bufs[vs] : nullptr, value_bytes ? val_bufs[vs ^ 1] : nullptr};
+  int flipped = 0;
+  const int r = b2s::segmented_impl(d_temp_storage, temp_storage_bytes, k, v, &flipped, true, num_items, num_segments,
+                                    d_begin_offsets, d_end_offsets, offset_bytes, key_type, value_bytes, descending != 0, begin_bit,
+                                    end_bit, (cudaStream_t)stream);
+  if (r == 0 && d_temp_storage) {
+    *key_selector = ks ^ flipped;
+    if (value_bytes) *val_selector = vs ^ flipped;
+  }
+  return r;
+}
+
+int b2s_digit_histogram(const void* d_keys, uint64_t num_items, int key_type, int descending, int begin_bit, int end_bit,
+                        uint64_t* d_offsets, b2s_stream_t stream) {
+  if (!d_offsets || key_type < 0 || key_type >= B2S_KEY_TYPE_COUNT || end_bit <= begin_bit) return (int)cudaErrorInvalidValue;
+  const b2s::KeyInfo ki = b2s::kKeyInfo[key_type];
+  const int passes = (end_bit - begin_bit + 7) / 8;
+  const b2s::KernelSet* ks = b2s::kernels_for(ki.bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t) * ((size_t)passes * 256 + 1), s);
+  if (e != cudaSuccess || num_items == 0) return (int)e;
+  b2s::HistArgs h{};
+  h.keys = d_keys;
+  h.n = num_items;
+  h.dc = b2s::make_consts(ki, descending != 0);
+  h.begin_bit = begin_bit;
+  h.end_bit = end_bit;
+  h.num_passes = passes;
+  h.ghist = d_offsets;
+  h.done = reinterpret_cast<unsigned int*>(d_offsets + (size_t)passes * 256);
+  h.off64 = true;
+  const uint64_t vecs = (num_items * ki.bytes + 16 * 1024 - 1) / (16 * 1024);
+  uint64_t g = (uint64_t)b2s::sm_count();
+  if (g > vecs) g = vecs ? vecs : 1;
+  h.grid = (int)g;
+  return (int)ks->hist(h, s);
 }
 
 int b2s_key_bytes(int key_type) {

@@ -57,6 +57,23 @@ struct SingleArgs {
   int vbytes;
 };
 
+// Segmented sort (b2s_segmented.cuh): one CTA per segment, all passes in one launch.
+struct SegmentedArgs {
+  const void* keys_src;
+  void* keys_a;  // the last pass lands here
+  void* keys_b;  // the other ping-pong buffer
+  const void* vals_src;
+  void* vals_a;
+  void* vals_b;
+  const void* begin_offsets;
+  const void* end_offsets;
+  int offset_bytes;  // 4 or 8: element type of the offset arrays
+  uint64_t num_segments;
+  DigitConsts dc;
+  int begin_bit, end_bit, passes;
+  int vbytes;
+};
+
 // Multi-GPU partition pass (b2s_split): destination = number of splitters ordering at or before the key.
 constexpr int kMaxSplitters = 7;
 struct SplitArgs {
@@ -94,6 +111,7 @@ struct Variant {
   cudaError_t split_launch_k##K(const SplitArgs& a, cudaStream_t s);                          \
   int split_tile_k##K(int vbytes);                                                            \
   cudaError_t single_launch_k##K(const SingleArgs& a, cudaStream_t s);                        \
+  cudaError_t segmented_launch_k##K(const SegmentedArgs& a, cudaStream_t s);                  \
   int single_tile_items_k##K(int vbytes);
 B2S_DECL_K(1)
 B2S_DECL_K(2)

@@ -11,6 +11,7 @@
 #ifdef B2S_TUNING
 #include "b2s_onesweep.cuh"  // laboratory kernel: tuning library only
 #endif
+#include "b2s_segmented.cuh"
 #include "b2s_single_tile.cuh"
 #include "b2s_split.cuh"
 
@@ -296,6 +297,47 @@ cudaError_t single_v(const SingleArgs& a, cudaStream_t s) {
   return single_one<V, false>(a, s);
 }
 
+// ---- segmented sort ------------------------------------------------------------------------------------------------
+template <int V, bool F, typename SegOffT>
+cudaError_t segmented_one(const SegmentedArgs& a, cudaStream_t s) {
+  using S = TileSmem<K, V, SEG_NT, SEG_IPT>;
+  SegmentedParams<K, F> p;
+  p.keys_src = a.keys_src;
+  p.keys_a = a.keys_a;
+  p.keys_b = a.keys_b;
+  p.vals_src = a.vals_src;
+  p.vals_a = a.vals_a;
+  p.vals_b = a.vals_b;
+  p.begin_offsets = a.begin_offsets;
+  p.end_offsets = a.end_offsets;
+  p.pad_key = a.dc.pad_key;
+  p.op = make_op<F>(a.dc, a.begin_bit, 8);
+  p.begin_bit = a.begin_bit;
+  p.end_bit = a.end_bit;
+  p.passes = a.passes;
+  p.ones = 0xffffffffu;
+  auto kern = segmented_sort_kernel<K, V, F, SegOffT>;
+  cudaError_t e = ensure_smem(kern, S::TOTAL);
+  if (e != cudaSuccess) return e;
+  // one CTA per segment; grids beyond 2^31 - 1 segments are split
+  for (uint64_t first = 0; first < a.num_segments; first += 0x7fffffffull) {
+    const uint64_t count = a.num_segments - first < 0x7fffffffull ? a.num_segments - first : 0x7fffffffull;
+    p.begin_offsets = reinterpret_cast<const SegOffT*>(a.begin_offsets) + first;
+    p.end_offsets = reinterpret_cast<const SegOffT*>(a.end_offsets) + first;
+    kern<<<(unsigned int)count, SEG_NT, S::TOTAL, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+template <int V>
+cudaError_t segmented_v(const SegmentedArgs& a, cudaStream_t s) {
+  if constexpr (K >= 2) {
+    if (a.dc.is_float)
+      return a.offset_bytes == 8 ? segmented_one<V, true, long long>(a, s) : segmented_one<V, true, int>(a, s);
+  }
+  return a.offset_bytes == 8 ? segmented_one<V, false, long long>(a, s) : segmented_one<V, false, int>(a, s);
+}
+
 // ---- multi-GPU partition pass (4- and 8-byte keys; values 0/4/8 bytes) -----------------------
 #if (B2S_K == 4 || B2S_K == 8)
 constexpr int SPLIT_NT = 512;
@@ -358,13 +400,13 @@ cudaError_t split_v(const SplitArgs& a, cudaStream_t s) {
 
 template <bool F>
 cudaError_t split_count_one(const SplitArgs& a, cudaStream_t s) {
-  const unsigned long long per_cta = 1024ull * 16;
+  const unsigned long long per_cta = 512ull * 16 * (16 / K);
   unsigned long long grid = (a.pass.n + per_cta - 1) / per_cta;
   if (grid > 148ull * 4) grid = 148ull * 4;
   if (grid == 0) grid = 1;
-  split_count_kernel<K, SplitterOp<K, F>><<<(unsigned int)grid, 1024, 0, s>>>(a.pass.keys_in, a.pass.n,
-                                                                            make_splitter_op<F>(a),
-                                                                            reinterpret_cast<unsigned long long*>(a.counts));
+  split_count_kernel<K, SplitterOp<K, F>><<<(unsigned int)grid, 512, 0, s>>>(a.pass.keys_in, a.pass.n,
+                                                                           make_splitter_op<F>(a),
+                                                                           reinterpret_cast<unsigned long long*>(a.counts));
   return cudaGetLastError();
 }
 #endif
@@ -404,6 +446,20 @@ cudaError_t CAT(single_launch_k, B2S_K)(const SingleArgs& a, cudaStream_t s) {
     case 1: return single_v<1>(a, s);
     case 2: return single_v<2>(a, s);
     case 16: return single_v<16>(a, s);
+#endif
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t CAT(segmented_launch_k, B2S_K)(const SegmentedArgs& a, cudaStream_t s) {
+  switch (a.vbytes) {
+    case 0: return segmented_v<0>(a, s);
+    case 4: return segmented_v<4>(a, s);
+    case 8: return segmented_v<8>(a, s);
+#ifndef B2S_TUNING
+    case 1: return segmented_v<1>(a, s);
+    case 2: return segmented_v<2>(a, s);
+    case 16: return segmented_v<16>(a, s);
 #endif
     default: return cudaErrorInvalidValue;
   }

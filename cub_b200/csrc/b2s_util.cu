@@ -3,6 +3,7 @@
 // oracle, and a bit-ordered lower_bound used by the multi-GPU splitter step.
 #include <cuda_runtime.h>
 
+#include "../../include/b2s_mgpu.h"
 #include "../../include/b2s_radix_sort.h"
 #include "b2s_common.cuh"
 
@@ -97,6 +98,20 @@ __global__ void check_sorted_kernel(const void* keys, const void* vals, unsigned
   }
 }
 
+// adjacent positions with equal sort keys whose values do not increase (values = input indices: 0 for a stable sort)
+__global__ void check_stable_kernel(const void* keys, const void* vals, unsigned long long n, int kbytes, int vbytes,
+                                    TypeConsts c, unsigned long long* result) {
+  unsigned long long bad = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += stride) {
+    if (sort_key(load_any(keys, i, kbytes), c) == sort_key(load_any(keys, i + 1, kbytes), c) &&
+        load_any(vals, i, vbytes) >= load_any(vals, i + 1, vbytes))
+      bad++;
+  }
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(result, bad);
+}
+
 __global__ void lower_bound_kernel(const void* keys, unsigned long long n, int kbytes, TypeConsts c,
                                    const void* splitters, int num, unsigned long long* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,6 +187,21 @@ int b2s_fill_iota(void* d_values, uint64_t n, int value_bytes, uint64_t first_in
     case 8: fill_iota_kernel<<<g, 256, 0, s>>>((unsigned long long*)d_values, n, first_index); break;
     default: return (int)cudaErrorInvalidValue;
   }
+  return (int)cudaGetLastError();
+}
+
+int b2s_check_stable(const void* d_keys, const void* d_values, uint64_t n, int key_type, int value_bytes, int descending,
+                     int begin_bit, int end_bit, uint64_t* d_result, b2s_stream_t stream) {
+  using namespace b2s;
+  TypeConsts c;
+  if (!make_type_consts(key_type, descending, begin_bit, end_bit, &c) || !d_values || !(value_bytes == 4 || value_bytes == 8))
+    return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(d_result, 0, sizeof(uint64_t), s);
+  if (e != cudaSuccess) return (int)e;
+  if (n < 2) return 0;
+  check_stable_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_keys, d_values, n, kBytes[key_type], value_bytes, c,
+                                                       reinterpret_cast<unsigned long long*>(d_result));
   return (int)cudaGetLastError();
 }
 

@@ -20,9 +20,13 @@ source rank).  Algorithm (sample sort around the local LSD sort):
   4. local sort  one stable DeviceRadixSort (DoubleBuffer form) over what was received.  Runs arrive in rank order
                  and the sort is stable, so equal keys end up in (rank, index) order.
 
-torch.distributed carries only metadata (samples, counts, barriers) plus, for exchange="nccl", the payload.
-All device work goes through the C-ABI of libb2s.so (`LocalOps`); tests substitute a CPU `LocalOps` built on the
-oracle to exercise this host logic under gloo -- the product has no CPU path.
+Two hosts drive the same kernels:
+  * `NativeDistributedSorter` (the product path on GPUs): a thin binding of the C++ host inside libb2s.so
+    (include/b2s_mgpu.h, cub_b200/csrc/b2s_mgpu.cu): NCCL called from C++ for the metadata, cudaIpc* peer mappings,
+    everything enqueued on one stream; torch.distributed is used once, to hand the NCCL unique id to the ranks.
+  * `DistributedSorter`: the same algorithm orchestrated from Python over torch.distributed (metadata, and the payload
+    for exchange="nccl").  All device work goes through the C-ABI of libb2s.so (`LocalOps`); tests substitute a CPU
+    `LocalOps` built on the oracle to exercise this host logic under gloo -- the product has no CPU path.
 """
 from __future__ import annotations
 
@@ -191,8 +195,21 @@ class LocalOps:
         return [int(x) for x in res.cpu().tolist()]
 
 
+    def check_stable(self, keys, vals, n, key_type, descending, begin_bit, end_bit) -> int:
+        """Adjacent positions with equal sort keys whose values do not increase (0 for a stable sort of (key, index))."""
+        res = torch.zeros(1, dtype=torch.int64, device=self.device)
+        err = self.lib.b2s_check_stable(ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(vals.data_ptr()), n, key_type,
+                                        vals.element_size(), int(descending), begin_bit, end_bit,
+                                        ctypes.c_void_p(res.data_ptr()), self._stream())
+        if err:
+            raise RuntimeError(f"b2s_check_stable failed: cudaError {err}")
+        return int(res.item())
+
+
 @dataclass
 class SortedShard:
+    """NOTE: keys / values are VIEWS of the sorter's receive buffers: the next sort() on any rank overwrites them
+    (peers store into these buffers).  Clone what must outlive the next call."""
     keys: torch.Tensor            # this rank's part of the globally sorted sequence (length = count)
     values: Optional[torch.Tensor]
     count: int
@@ -244,7 +261,6 @@ class DistributedSorter:
         self.samples_per_rank = samples_per_rank
         self.capacity = int(n_local * slack) + 1024  # the same on every rank (n_local is the common maximum shard size)
         self.temp: dict = {}
-        self._sizes_for, self._all_n = None, None
         self._fence = self.ops.empty(1, torch.int32).zero_()
         self._phase_ms: dict = {}
         self._launches = 0
@@ -328,18 +344,14 @@ class DistributedSorter:
         t0 = time.perf_counter()
 
         # 1. samples -> splitters (identical on every rank)
-        if self._sizes_for != n:  # shard sizes are exchanged once per distinct local size (collective: all ranks re-enter)
-            sizes = torch.tensor([n], dtype=torch.int64, device=self.device)
-            all_sizes = torch.zeros(G, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(all_sizes, sizes, group=self.group)
-            self._all_n = [int(x) for x in all_sizes.cpu().tolist()]
-            self._sizes_for = n
-        all_n = self._all_n
-        if min(all_n) < 1:
+        # Every rank contributes exactly `samples_per_rank` regularly spaced samples whatever its shard size (indices
+        # repeat when n < samples_per_rank), so no rank needs to know the others' sizes before sampling and every
+        # call issues the same sequence of collectives -- shard sizes may change freely between calls.
+        if n < 1:
             raise ValueError("every rank must hold at least one item")
-        s = min(self.samples_per_rank, min(all_n))
-        stride = n // s
-        sample = kin[: stride * s : stride].contiguous()
+        s = self.samples_per_rank
+        pick = (torch.arange(s, device=self.device, dtype=torch.int64) * n) // s
+        sample = kin[pick].contiguous()
         gathered = ops.empty(G * s, kin.dtype)
         dist.all_gather_into_tensor(gathered, sample, group=self.group)
         src = torch.arange(G, dtype=torch.int32, device=self.device).repeat_interleave(s)
@@ -371,6 +383,9 @@ class DistributedSorter:
         else:
             matrix = dmatrix.cpu().numpy()
             send_counts, send_offsets, recv_counts, total, _peer_offsets = exchange_plan(matrix, me)
+            worst = int(matrix.sum(axis=0).max())
+            if worst > self.capacity:  # the same matrix on every rank: every rank raises BEFORE the collective
+                raise RuntimeError(f"receive capacity {self.capacity} too small for {worst} items; raise `slack`")
             send_offsets_dev = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
             ops.split_scatter(kin, vin, self.part_k, self.part_v, n, kt, desc, bb, eb, sp_keys, sp_ranks, me,
                               send_offsets_dev, None, None, self.temp)
@@ -402,34 +417,163 @@ class DistributedSorter:
         out_k = ok[:total].view(self.key_dtype) if ok.dtype != self.key_dtype else ok[:total]
         return SortedShard(out_k, ov[:total] if ov is not None else None, total, out_counts)
 
-    # ---- verification at any size: local order, cross-rank boundaries, global multiset
-    def verify(self, keys_in: torch.Tensor, values_in: Optional[torch.Tensor], out: SortedShard) -> bool:
-        ops, G = self.ops, self.world
-        kt, desc, bb, eb = self.key_type, self.descending, self.begin_bit, self.end_bit
-        inv_out, ksum_out, psum_out = ops.check_sorted(self._container(out.keys), out.values, out.count, kt, desc, bb, eb) \
-            if out.count else (0, 0, 0)
-        _inv, ksum_in, psum_in = ops.check_sorted(self._container(keys_in), values_in, keys_in.numel(), kt, desc, bb, eb)
-        sums = torch.tensor([ksum_in, psum_in, ksum_out, psum_out, keys_in.numel(), out.count], dtype=torch.int64,
-                            device=self.device)
-        dist.all_reduce(sums, group=self.group)  # int64 wraps mod 2^64 like the checksums
-        sums = sums.cpu().tolist()
-        ok = inv_out == 0 and sums[0] == sums[2] and sums[1] == sums[3] and sums[4] == sums[5]
-        edge = torch.zeros(3, dtype=torch.int64, device=self.device)
-        if out.count:
-            kc = self._container(out.keys)
-            edge[0] = 1
-            edge[1] = kc[0].to(torch.int64)
-            edge[2] = kc[out.count - 1].to(torch.int64)
-        edges = [torch.zeros_like(edge) for _ in range(G)]
-        dist.all_gather(edges, edge, group=self.group)
-        last = None
-        for e in edges:
-            has, first_raw, last_raw = (int(x) for x in e.cpu().tolist())
-            if not has:
-                continue
-            if last is not None and sort_key(last, kt, desc, bb, eb) > sort_key(first_raw, kt, desc, bb, eb):
+    def verify(self, keys_in: torch.Tensor, values_in: Optional[torch.Tensor], out: SortedShard,
+               values_are_global_indices: bool = False) -> bool:
+        return verify_global_sort(self.ops, self.group, self.world, self._container(keys_in), values_in,
+                                  self._container(out.keys), out.values, out.count, self.key_type, self.descending,
+                                  self.begin_bit, self.end_bit, values_are_global_indices)
+
+
+def verify_global_sort(ops, group, world, keys_in, values_in, keys_out, values_out, count, key_type, descending, begin_bit,
+                       end_bit, values_are_global_indices=False) -> bool:
+    """Verification at any size (collective): local order, cross-rank boundaries, global multiset of keys and of
+    (key, value) pairs.  With `values_are_global_indices` (values increase along the rank-order concatenation of the
+    input, e.g. rank * n + i) also STABILITY: inside every run of equal sort keys the values increase, within a rank
+    (device kernel) and across rank boundaries (last item of a rank against the first item of the next)."""
+    G = world
+    device = ops.device
+    kt, desc, bb, eb = key_type, descending, begin_bit, end_bit
+    inv_out, ksum_out, psum_out = ops.check_sorted(keys_out, values_out, count, kt, desc, bb, eb) if count else (0, 0, 0)
+    _inv, ksum_in, psum_in = ops.check_sorted(keys_in, values_in, keys_in.numel(), kt, desc, bb, eb)
+    unstable = 0
+    stable_check = values_are_global_indices and values_out is not None and hasattr(ops, "check_stable")
+    if stable_check and count > 1:
+        unstable = ops.check_stable(keys_out, values_out, count, kt, desc, bb, eb)
+    sums = torch.tensor([ksum_in, psum_in, ksum_out, psum_out, keys_in.numel(), count], dtype=torch.int64, device=device)
+    dist.all_reduce(sums, group=group)  # int64 wraps mod 2^64 like the checksums
+    sums = sums.cpu().tolist()
+    ok = inv_out == 0 and unstable == 0 and sums[0] == sums[2] and sums[1] == sums[3] and sums[4] == sums[5]
+    edge = torch.zeros(5, dtype=torch.int64, device=device)
+    if count:
+        edge[0] = 1
+        edge[1] = keys_out[0].to(torch.int64)
+        edge[2] = keys_out[count - 1].to(torch.int64)
+        if values_out is not None:
+            edge[3] = values_out[0].to(torch.int64)
+            edge[4] = values_out[count - 1].to(torch.int64)
+    edges = [torch.zeros_like(edge) for _ in range(G)]
+    dist.all_gather(edges, edge, group=group)
+    last = None
+    vmask = (1 << (8 * values_out.element_size())) - 1 if values_out is not None else 0
+    for e in edges:
+        has, first_raw, last_raw, first_val, last_val = (int(x) for x in e.cpu().tolist())
+        if not has:
+            continue
+        if last is not None:
+            a, b = sort_key(last[0], kt, desc, bb, eb), sort_key(first_raw, kt, desc, bb, eb)
+            if a > b or (stable_check and a == b and (last[1] & vmask) >= (first_val & vmask)):
                 ok = False
-            last = last_raw
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=self.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        return bool(flag.item())
+        last = (last_raw, last_val)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
+class _DevicePointerView:
+    """Zero-copy torch view of device memory owned by libb2s.so (through __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TYPESTR = {torch.int32: "<i4", torch.int64: "<i8"}
+
+
+class NativeDistributedSorter:
+    """The product multi-GPU sorter: binding of the C++ host in libb2s.so (include/b2s_mgpu.h).  One process per GPU;
+    `group` (any torch.distributed backend) is used once, to broadcast the NCCL unique id, and by verify()."""
+
+    def __init__(self, n_local: int, key_dtype: torch.dtype, value_dtype: Optional[torch.dtype] = None, group=None,
+                 descending: bool = False, begin_bit: int = 0, end_bit: Optional[int] = None, samples_per_rank: int = 8192,
+                 slack: float = 1.10, device: Optional[torch.device] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.key_type = key_type_of(key_dtype)
+        self.kbytes = KEY_BYTES[self.key_type]
+        self.key_dtype, self.value_dtype = key_dtype, value_dtype
+        self.vbytes = torch.empty(0, dtype=value_dtype).element_size() if value_dtype is not None else 0
+        self.descending, self.begin_bit = descending, begin_bit
+        self.end_bit = self.kbytes * 8 if end_bit is None else end_bit
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.ops = LocalOps(device)
+        self.device = device
+        self.lib = self.ops.lib
+        self.n_local = n_local
+        self.exchange = "peer"
+        ident = [None]
+        if self.rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            err = self.lib.b2s_mgpu_unique_id(buf)
+            if err:
+                raise RuntimeError(f"b2s_mgpu_unique_id failed: {err} (2001 = libnccl.so.2 not found)")
+            ident[0] = bytes(buf.raw)
+        if self.world > 1:
+            dist.broadcast_object_list(ident, src=0, group=group)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            err = self.lib.b2s_mgpu_create(ctypes.byref(self._h), ident[0], self.rank, self.world, n_local, self.key_type,
+                                           self.vbytes, int(descending), begin_bit, self.end_bit, float(slack), samples_per_rank)
+        if err:
+            msg = self.lib.b2s_mgpu_last_error(self._h).decode() if self._h else ""
+            raise RuntimeError(f"b2s_mgpu_create failed: {err} {msg}")
+        self.capacity = int(self.lib.b2s_mgpu_capacity(self._h))
+        self._launches = 0
+
+    def close(self):
+        if self._h:
+            with torch.cuda.device(self.device):
+                self.lib.b2s_mgpu_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def _container(self, t: torch.Tensor) -> torch.Tensor:
+        return t.view(_CONTAINER[t.element_size()]) if t.dtype not in (torch.int8, torch.int16, torch.int32, torch.int64) else t
+
+    def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None) -> SortedShard:
+        """Collective.  Returns views of the library's receive buffers (see SortedShard)."""
+        n = keys.numel()
+        if (values is None) != (self.value_dtype is None):
+            raise ValueError("values must be given iff the sorter was built with a value dtype")
+        if keys.device != self.device or (values is not None and values.device != self.device):
+            raise ValueError("shards must live on the sorter's device")
+        ko, vo = ctypes.c_void_p(), ctypes.c_void_p()
+        cnt = ctypes.c_uint64(0)
+        counts = (ctypes.c_uint64 * MAX_RANKS)()
+        with torch.cuda.device(self.device):
+            err = self.lib.b2s_mgpu_sort(self._h, ctypes.c_void_p(keys.data_ptr()),
+                                         ctypes.c_void_p(values.data_ptr()) if values is not None else None, n,
+                                         ctypes.byref(ko), ctypes.byref(vo), ctypes.byref(cnt), counts,
+                                         ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if err:
+            raise RuntimeError(f"b2s_mgpu_sort failed: {err} {self.lib.b2s_mgpu_last_error(self._h).decode()}")
+        total = int(cnt.value)
+        kc = _CONTAINER[self.kbytes]
+        out_k = torch.as_tensor(_DevicePointerView(ko.value, max(total, 1), _TYPESTR[kc]), device=self.device)[:total]
+        out_k = out_k.view(self.key_dtype) if out_k.dtype != self.key_dtype else out_k
+        out_v = None
+        if values is not None:
+            vc = _CONTAINER[self.vbytes]
+            out_v = torch.as_tensor(_DevicePointerView(vo.value, max(total, 1), _TYPESTR[vc]), device=self.device)[:total]
+            out_v = out_v.view(self.value_dtype) if out_v.dtype != self.value_dtype else out_v
+        self._launches = 1 + 1 + 8 + 2 + 3 + 1 + (1 + 1 + self.kbytes)  # kernels + memsets enqueued per call (nominal)
+        return SortedShard(out_k, out_v, total, [int(counts[d]) for d in range(self.world)])
+
+    def last_phase_ms(self):
+        ms = (ctypes.c_float * 6)()
+        sent = ctypes.c_uint64(0)
+        err = self.lib.b2s_mgpu_last_phases(self._h, ms, ctypes.byref(sent))
+        if err:
+            return {}
+        return {"splitters": ms[0], "count+plan": ms[1], "partition_kernel_device_ms": ms[2], "fence": ms[3],
+                "local_sort": ms[4], "whole_call_device_ms": ms[5], "items_sent_to_peers": int(sent.value),
+                "exchange": "peer (C++ host, bulk shared->peer copies)", "timing": "CUDA events on the sort's stream"}
+
+    def launches_per_sort(self):
+        return self._launches
+
+    def verify(self, keys_in: torch.Tensor, values_in: Optional[torch.Tensor], out: SortedShard,
+               values_are_global_indices: bool = False) -> bool:
+        return verify_global_sort(self.ops, self.group, self.world, self._container(keys_in), values_in,
+                                  self._container(out.keys), out.values, out.count, self.key_type, self.descending,
+                                  self.begin_bit, self.end_bit, values_are_global_indices)

@@ -93,6 +93,53 @@ int b2s_radix_sort_db(void *d_temp_storage, size_t *temp_storage_bytes,
                       uint64_t num_items, int key_type, int value_bytes, int offset_bytes,
                       int descending, int begin_bit, int end_bit, b2s_stream_t stream);
 
+/*
+ * User-defined key structs ("decomposer" overloads).  Replaces the 16 overloads
+ *   cub::DeviceRadixSort::{SortKeys,SortPairs}[Descending](..., decomposer [, begin_bit, end_bit], stream)
+ *   (device_radix_sort.cuh:486-530, 625-666, 922-962, 1055-1105, 1368-1426, 1515-1563, 1816-1856, 1949-...),
+ * pointer and DoubleBuffer forms.  The decomposer -- a callable returning a tuple of references to the arithmetic
+ * members of the key, MOST significant first -- is type-erased into `fields`: byte offset and fundamental type of every
+ * tuple element, in tuple order (the C++ veneer derives them by applying the decomposer to a probe object).
+ * The sort is the stable sort on bits [begin_bit, end_bit) of the concatenated bit-ordered image (bit 0 is in the LAST
+ * field); end_bit < 0 means "all bits" (the overloads without a bit range).  Keys are moved as opaque
+ * key_struct_bytes-byte records, values as opaque value_bytes-byte records (0 = keys only, up to 64).
+ * Same conventions as b2s_radix_sort; the temp storage holds one (u64 word, index) pair per item, twice.
+ */
+#define B2S_MAX_STRUCT_FIELDS 8
+typedef struct {
+  int32_t offset;   /* byte offset of the member inside the key struct */
+  int32_t key_type; /* b2s_key_t of the member */
+} b2s_field_t;
+int b2s_radix_sort_struct(void *d_temp_storage, size_t *temp_storage_bytes,
+                          const void *d_keys_in, void *d_keys_out, const void *d_values_in, void *d_values_out,
+                          uint64_t num_items, int key_struct_bytes, const b2s_field_t *fields, int num_fields,
+                          int value_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream);
+int b2s_radix_sort_struct_db(void *d_temp_storage, size_t *temp_storage_bytes,
+                             void *key_bufs[2], int *key_selector, void *val_bufs[2], int *val_selector,
+                             uint64_t num_items, int key_struct_bytes, const b2s_field_t *fields, int num_fields,
+                             int value_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream);
+
+/*
+ * Segmented sort: num_segments independent stable sorts of the contiguous ranges
+ * [d_begin_offsets[s], d_end_offsets[s]) of one array.  Replaces cub::DeviceSegmentedRadixSort::{SortKeys,SortPairs}
+ * [Descending], pointer and DoubleBuffer forms (cub/device/device_segmented_radix_sort.cuh; kernel
+ * dispatch_radix_sort.cuh:383, dispatch :2076).  The offset arrays are DEVICE arrays of offset_bytes-byte signed integers
+ * (4 or 8; the reference takes iterators -- int* in its tests and documentation); begin and end may alias
+ * (d_offsets, d_offsets + 1); segments with end <= begin are empty; items outside every segment are not written.
+ * One launch, one CTA per segment: segments of at most 4096 items are sorted entirely in shared memory.
+ * Conventions as b2s_radix_sort / b2s_radix_sort_db (begin_bit == end_bit copies every segment in the pointer form).
+ */
+int b2s_segmented_radix_sort(void *d_temp_storage, size_t *temp_storage_bytes,
+                             const void *d_keys_in, void *d_keys_out, const void *d_values_in, void *d_values_out,
+                             uint64_t num_items, uint64_t num_segments, const void *d_begin_offsets,
+                             const void *d_end_offsets, int offset_bytes, int key_type, int value_bytes, int descending,
+                             int begin_bit, int end_bit, b2s_stream_t stream);
+int b2s_segmented_radix_sort_db(void *d_temp_storage, size_t *temp_storage_bytes,
+                                void *key_bufs[2], int *key_selector, void *val_bufs[2], int *val_selector,
+                                uint64_t num_items, uint64_t num_segments, const void *d_begin_offsets,
+                                const void *d_end_offsets, int offset_bytes, int key_type, int value_bytes, int descending,
+                                int begin_bit, int end_bit, b2s_stream_t stream);
+
 /* Size in bytes of a key of the given type (0 for an invalid type). */
 int b2s_key_bytes(int key_type);
 
@@ -126,6 +173,13 @@ int b2s_set_single_tile(int enable);
 /* Scheduling mode of a variant: bits 0-1 = 0 one tile per CTA, 1/2 persistent CTAs (next tile claimed after/before the
  * write-out); bits 16+ = L2 prefetch distance in tiles.  -1 for an unknown variant. */
 int b2s_variant_mode(int key_bytes, int value_bytes, int variant);
+/* The upfront histogram kernel alone (replaces DeviceRadixSortHistogramKernel + DeviceRadixSortExclusiveSumKernel,
+ * dispatch_radix_sort.cuh:556,603): d_offsets[p * 256 + d] = number of keys whose digit of pass p (bits
+ * [begin_bit + 8p, min(begin_bit + 8p + 8, end_bit)) of the bit-ordered key) is < d.  d_offsets holds
+ * ceil((end_bit - begin_bit) / 8) * 256 + 1 uint64 (the last word is scratch).  Exposed so that tests can check the
+ * kernel directly against the oracle; a sort runs it internally. */
+int b2s_digit_histogram(const void *d_keys, uint64_t num_items, int key_type, int descending, int begin_bit, int end_bit,
+                        uint64_t *d_offsets, b2s_stream_t stream);
 /* Kernel and flow of a variant: >= 0 production kernel (b2s_pass.cuh) with these flag bits (1 = (key,value) scattered as
  * one 64-bit store, 2 = bulk-copy write-out, 4 = ticketed tile ids); -1 laboratory kernel (tuning builds); -2 unknown. */
 int b2s_variant_flow(int key_bytes, int value_bytes, int variant);
@@ -145,7 +199,8 @@ int b2s_set_trace(void *d_trace, int pass);
  * concatenation of the shards.  Keys: 4- or 8-byte types; values: 0, 4 or 8 bytes.
  *
  * Splitters are (raw key, source rank) pairs in DEVICE memory (they come out of a device-side sort of the samples, and
- * the host never has to wait for them), ascending in sort order; at most 7 (8 ranks).  The per-destination offsets
+ * the host never has to wait for them), ascending in (sort key, source rank) order -- what a stable sort of the
+ * (key, rank) samples produces; at most 7 (8 ranks).  The per-destination offsets
  * of b2s_split_scatter are in device memory as well: the whole exchange is enqueued without a host round trip.
  * A local key goes to destination d = number of splitters (k*, r*) with (k*, r*) <= (key, my_rank), comparing
  * keys on bits [begin_bit, end_bit) of their bit-ordered transform.

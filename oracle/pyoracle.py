@@ -127,11 +127,25 @@ def load_gpu_reference(which: str = "ref"):
     product_binding.bind(lib, prefix)
     lib.sort = getattr(lib, prefix + "_radix_sort")
     lib.sort_db = getattr(lib, prefix + "_radix_sort_db")
+    c = ctypes
+    if hasattr(lib, prefix + "_struct_sort"):  # oracle/ref_shim_ext.cu (reference build only)
+        lib.struct_sort = getattr(lib, prefix + "_struct_sort")
+        lib.struct_sort.restype = c.c_int
+        lib.struct_sort.argtypes = [c.c_void_p, c.POINTER(c.c_size_t), c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64,
+                                    c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
+        lib.segmented_sort = getattr(lib, prefix + "_segmented_sort")
+        lib.segmented_sort.restype = c.c_int
+        lib.segmented_sort.argtypes = [c.c_void_p, c.POINTER(c.c_size_t), c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64,
+                                       c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
+        lib.sort128 = getattr(lib, prefix + "_sort128")
+        lib.sort128.restype = c.c_int
+        lib.sort128.argtypes = [c.c_void_p, c.POINTER(c.c_size_t), c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64,
+                                c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
     return lib
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Decomposer (custom struct key) semantics -- checker for SURVEY.md §8(f)2, no product counterpart yet.
+# Decomposer (custom struct key) semantics -- checker for SURVEY.md §8(f)2 (product: cub_b200/csrc/b2s_struct.cu).
 # Reference: the decomposer overloads of cub::DeviceRadixSort (cub/device/device_radix_sort.cuh:486-530, 625-666, ...):
 # a key is a tuple of arithmetic fields; the sort key is the concatenation of the fields' bit-ordered images, first tuple
 # element most significant, LAST element holding bit 0 (test/catch2_test_device_radix_sort_custom.cu:1100-1115);
@@ -139,21 +153,28 @@ def load_gpu_reference(which: str = "ref"):
 # 1078, 1179), -0.0 compares equal to +0.0 in a floating field (radix_rank_sort_operations.cuh:79-89), descending inverts
 # the whole image (:592-599); the sort is stable.
 # ---------------------------------------------------------------------------------------------------------------------
-def _ordered_field(bits: np.ndarray, key_type: int) -> np.ndarray:
-    """Bit-ordered image of one field as uint64 (only the low 8*bytes bits are used)."""
+def _ordered_field(bits: np.ndarray, key_type: int, descending: bool = False) -> np.ndarray:
+    """Bit-ordered image of one field as uint64 (only the low 8*bytes bits are used), complemented when descending.
+    Floating fields: -0.0 and +0.0 share one image, HIGH in both directions, exactly as in the reference's onesweep path
+    (radix_rank_sort_operations.cuh:55-66, 79-89: ascending -0.0 is mapped onto +0.0, descending the complemented +0.0 onto
+    the complemented -0.0).  The reference's single-tile path (n <= 4864) maps onto +0.0 BEFORE reversing instead; the two
+    agree unless a partial bit range cuts through a floating field of a descending sort, and none of the 16 known-answer
+    vectors does (their zeros come with the full range)."""
     nbits = KEY_BYTES[key_type] * 8
     ones = (1 << nbits) - 1
     high = 1 << (nbits - 1)
     k = bits.astype(np.uint64)
     cat = KEY_CATEGORY[key_type]
-    if cat == 0:
-        return k
     if cat == 1:
-        return k ^ np.uint64(high)
-    neg_zero = k == np.uint64(high)
-    k = np.where(neg_zero, np.uint64(0), k)  # -0.0 orders (and is digit-extracted) as +0.0
-    sign = (k >> np.uint64(nbits - 1)) & np.uint64(1)
-    return k ^ np.where(sign == 1, np.uint64(ones), np.uint64(high))
+        k = k ^ np.uint64(high)
+    elif cat == 2:
+        sign = (k >> np.uint64(nbits - 1)) & np.uint64(1)
+        k = k ^ np.where(sign == 1, np.uint64(ones), np.uint64(high))
+    if descending:
+        k = k ^ np.uint64(ones)
+    if cat == 2:
+        k = np.where(k == np.uint64(ones ^ high), np.uint64(high), k)
+    return k
 
 
 def decomposed_sort_permutation(fields, descending=False, begin_bit=0, end_bit=None):
@@ -166,9 +187,7 @@ def decomposed_sort_permutation(fields, descending=False, begin_bit=0, end_bit=N
     keys = []
     lo = 0  # bit offset of the current field inside the concatenation, starting from the LAST field
     for (bits, kt), w in zip(reversed(fields), reversed(widths)):
-        img = _ordered_field(np.ascontiguousarray(bits), kt)
-        if descending:
-            img = img ^ np.uint64((1 << w) - 1)
+        img = _ordered_field(np.ascontiguousarray(bits), kt, descending)
         b, e = max(begin_bit, lo), min(end_bit, lo + w)
         if e > b:
             mask = ((1 << (e - lo)) - 1) ^ ((1 << (b - lo)) - 1)

@@ -58,6 +58,66 @@ int run(int n, bool descending) {
   return 0;
 }
 
+// User-defined key struct with a decomposer, shaped like the reference's documentation example
+// (cub/device/device_radix_sort.cuh:128-195: custom_t { float f; long long lli; } + decomposer_t).
+struct custom_t {
+  float f;
+  long long lli;
+};
+struct decomposer_t {
+  __host__ __device__ ::cuda::std::tuple<float&, long long&> operator()(custom_t& key) const { return {key.f, key.lli}; }
+};
+
+int run_struct(int n) {
+  std::vector<custom_t> h(n);
+  std::vector<int> h_vals(n);
+  unsigned s = 777u;
+  for (int i = 0; i < n; ++i) {
+    s = s * 1664525u + 1013904223u;
+    h[i].f = (float)((int)(s >> 24) - 128) / 4.0f;  // few distinct values: the second member decides often
+    s = s * 1664525u + 1013904223u;
+    h[i].lli = (long long)(int)s * 1000003ll;
+    h_vals[i] = i;
+  }
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return h[a].f < h[b].f || (h[a].f == h[b].f && h[a].lli < h[b].lli);
+  });
+  custom_t *d_in, *d_out; int *d_vin, *d_vout;
+  CK(cudaMalloc(&d_in, n * sizeof(custom_t))); CK(cudaMalloc(&d_out, n * sizeof(custom_t)));
+  CK(cudaMalloc(&d_vin, n * sizeof(int))); CK(cudaMalloc(&d_vout, n * sizeof(int)));
+  CK(cudaMemcpy(d_in, h.data(), n * sizeof(custom_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_vin, h_vals.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  void* d_temp_storage = nullptr; size_t temp_storage_bytes = 0;
+  CK(b200::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, d_in, d_out, d_vin, d_vout, n, decomposer_t{}));
+  CK(cudaMalloc(&d_temp_storage, temp_storage_bytes));
+  CK(b200::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, d_in, d_out, d_vin, d_vout, n, decomposer_t{}));
+  std::vector<int> got(n);
+  std::vector<custom_t> gk(n);
+  CK(cudaMemcpy(got.data(), d_vout, n * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(gk.data(), d_out, n * sizeof(custom_t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    if (got[i] != order[i] || gk[i].f != h[order[i]].f || gk[i].lli != h[order[i]].lli) { printf("decomposer form mismatch at %d\n", i); return 1; }
+  // descending, keys only, DoubleBuffer form, explicit bit range covering the whole 96-bit image
+  b200::DoubleBuffer<custom_t> d_keys(d_in, d_out);
+  CK(b200::DeviceRadixSort::SortKeysDescending(d_temp_storage, temp_storage_bytes, d_keys, n, decomposer_t{}, 0, 96));
+  CK(cudaMemcpy(gk.data(), d_keys.Current(), n * sizeof(custom_t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) {
+    const custom_t& e = h[order[n - 1 - i]];  // all (f, lli) pairs are distinct with overwhelming probability: reverse order
+    if (gk[i].f != e.f || gk[i].lli != e.lli) { printf("decomposer descending mismatch at %d\n", i); return 1; }
+  }
+  // the deprecated debug_synchronous overload still compiles and sorts
+  unsigned *d_u, *d_u2;
+  CK(cudaMalloc(&d_u, 1000 * sizeof(unsigned))); CK(cudaMalloc(&d_u2, 1000 * sizeof(unsigned)));
+  CK(cudaMemset(d_u, 0, 1000 * sizeof(unsigned)));
+  size_t tb = 0;
+  CK(b200::DeviceRadixSort::SortKeys(nullptr, tb, d_u, d_u2, 1000, 0, 32, 0, true));
+  cudaFree(d_u); cudaFree(d_u2);
+  cudaFree(d_temp_storage); cudaFree(d_in); cudaFree(d_out); cudaFree(d_vin); cudaFree(d_vout);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   int n = argc > 1 ? atoi(argv[1]) : 1000003;
   int rc = 0;
@@ -65,6 +125,7 @@ int main(int argc, char** argv) {
   rc |= run<int>(n, true);
   rc |= run<unsigned long long>(n / 3, false);
   rc |= run<double>(n / 5, true);
+  rc |= run_struct(n / 2);
   printf(rc == 0 ? "veneer example: OK\n" : "veneer example: FAILED\n");
   return rc;
 }

@@ -11,9 +11,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "b2s_radix_sort.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", text)))
+    """Every function declared by the C headers in include/ (b2s_radix_sort.h, b2s_mgpu.h, ...)."""
+    import glob
+
+    syms = set()
+    for path in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        syms |= set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", text))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol(b2s):

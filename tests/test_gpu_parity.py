@@ -428,3 +428,105 @@ def test_cuda_graph_capture_and_replay(b2s, oracle, n):
         ek, ev = oracle.radix_sort(raw, v, 7)  # the tensors are int32: signed order
         assert np.array_equal(H.to_np(keys_out, np.uint32), ek), f"graph replay {rep}: keys differ"
         assert np.array_equal(H.to_np(vals_out, np.uint32), ev), f"graph replay {rep}: values differ"
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: the survey's "unpinned corner" -- floating keys x partial bit ranges x direction -- against the reference
+# ---------------------------------------------------------------------------------------------
+FLOAT_PARTIAL = [(8, 4), (5, 2), (11, 8), (4, 2)]  # (key type, bytes): f32, bf16, f64, f16
+
+
+@pytest.mark.parametrize("kt,nb", FLOAT_PARTIAL, ids=[H.KEY_NAMES[k] for k, _ in FLOAT_PARTIAL])
+@pytest.mark.parametrize("n", [1000, 4864, 4865, (1 << 20) + 77])
+def test_float_partial_bit_ranges_vs_reference(b2s, refcub, oracle, kt, nb, n):
+    """Floating keys with [begin_bit, end_bit) != the whole key, both directions, with +-0 / NaN / inf / denormals.
+    The reference's two back-ends DISAGREE here when descending (radix_rank_sort_operations.cuh:55-66): its onesweep path
+    (n > 4864) maps both zeros to the complemented image of -0.0, its single-tile path (n <= 4864) to the image of +0.0
+    before reversing the order, so the zeros' digits of a PARTIAL range differ.  This library follows the onesweep
+    behaviour at every size: bit-exact with the reference for n > 4864 in both directions and for
+    n <= 4864 ascending; for n <= 4864 descending the checker is the oracle (onesweep semantics), and the reference is
+    still matched on the same input with its zeros replaced (no +-0 => the two reference paths agree)."""
+    bits = nb * 8
+    rng = np.random.default_rng(1000 * kt + n % 997)
+    raw = H.spice_floats(H.random_bits(rng, n, nb), nb)
+    vals = np.arange(n, dtype=np.uint32)
+    ranges = [(1, bits - 1), (0, bits - 1), (bits - 9, bits), (3, 12), (bits // 2 - 1, bits // 2 + 1)]
+    for bb, eb in ranges:
+        for desc in (False, True):
+            dk, dv = H.to_dev(raw), H.to_dev(vals)
+            k_us, v_us = H.sort_ptr(b2s.b2s_radix_sort, dk, dv, kt, desc, bb, eb)
+            ek, ev = oracle.radix_sort(raw, vals, kt, desc, bb, eb)
+            assert np.array_equal(H.to_np(k_us, raw.dtype), ek), f"vs oracle: {H.KEY_NAMES[kt]} n={n} [{bb},{eb}) desc={desc}"
+            assert np.array_equal(H.to_np(v_us, np.uint32), ev)
+            if n > 4864 or not desc:
+                k_ref, v_ref = H.sort_ptr(refcub.sort, dk, dv, kt, desc, bb, eb)
+                assert torch.equal(k_us, k_ref) and torch.equal(v_us, v_ref), \
+                    f"vs reference CUB: {H.KEY_NAMES[kt]} n={n} [{bb},{eb}) desc={desc}"
+            else:
+                nz = raw.copy()
+                high = np.array(1 << (bits - 1), dtype=np.uint64).astype(raw.dtype)
+                nz[(raw == 0) | (raw == high)] = 1  # smallest denormal instead of +-0
+                dk2 = H.to_dev(nz)
+                k_us2, v_us2 = H.sort_ptr(b2s.b2s_radix_sort, dk2, dv, kt, desc, bb, eb)
+                k_ref2, v_ref2 = H.sort_ptr(refcub.sort, dk2, dv, kt, desc, bb, eb)
+                assert torch.equal(k_us2, k_ref2) and torch.equal(v_us2, v_ref2), \
+                    f"vs reference CUB without zeros: {H.KEY_NAMES[kt]} n={n} [{bb},{eb}) desc"
+
+
+@pytest.mark.parametrize("kt", [6, 7, 8, 9, 11, 2, 5, 0, 1])
+def test_histogram_kernel_vs_oracle(b2s, oracle, kt):
+    """The upfront histogram kernel alone (b2s_histogram.cuh) against oracle_histogram: exclusive digit offsets of every
+    pass, whole keys and partial ranges, both directions, sizes around the vector / CTA granularity."""
+    nb = H.KEY_BYTES[kt]
+    bits = nb * 8
+    rng = np.random.default_rng(4000 + kt)
+    for n in (1, 15, 4097, 1_000_003):
+        raw = H.random_bits(rng, n, nb)
+        if kt in (5, 8, 11):
+            raw = H.spice_floats(raw, nb)
+        dk = H.to_dev(raw)
+        for bb, eb in ((0, bits), (1, bits - 1), (3, min(bits, 14))):
+            for desc in (False, True):
+                passes = (eb - bb + 7) // 8
+                out = torch.empty(passes * 256 + 1, dtype=torch.int64, device="cuda")
+                rc = b2s.b2s_digit_histogram(H._p(dk), n, kt, int(desc), bb, eb, H._p(out), H.stream_handle())
+                assert rc == 0
+                torch.cuda.synchronize()
+                got = out[: passes * 256].cpu().numpy().view(np.uint64).reshape(passes, 256)
+                counts = oracle.histogram(raw, kt, desc, bb, eb).reshape(passes, 256)
+                excl = np.cumsum(counts, axis=1) - counts
+                assert np.array_equal(got, excl), f"histogram {H.KEY_NAMES[kt]} n={n} [{bb},{eb}) desc={desc}"
+
+
+def test_lookback_forward_progress_under_concurrency(b2s, refcub):
+    """Decoupled look-back stress: several multi-thousand-tile sorts in flight at once on different streams (their CTAs
+    interleave on the SMs, so a tile's predecessors are NOT all resident when it starts), with block-index tile ids and
+    with ticketed ids (b2s_set_tile_claim).  Every result must be bit-exact; a lost-progress bug would hang (the test
+    runs under the suite's timeout)."""
+    n = (1 << 24) + 4321
+    keys = [H.gen_device_keys(b2s, n, 4, seed=50 + i) for i in range(4)]
+    vals = H.gen_device_iota(b2s, n, 4)
+    expect = [H.sort_ptr(refcub.sort, k, vals, 6) for k in keys]
+    for claim in (0, 1):
+        old = b2s.b2s_set_tile_claim(claim)
+        try:
+            streams = [torch.cuda.Stream() for _ in keys]
+            outs = []
+            nbytes = ctypes.c_size_t(0)
+            assert b2s.b2s_radix_sort(None, ctypes.byref(nbytes), None, None, None, None, n, 6, 4, 4, 0, 0, 32, None) == 0
+            temps = [torch.empty(nbytes.value, dtype=torch.uint8, device="cuda") for _ in keys]
+            torch.cuda.synchronize()
+            for rep in range(3):
+                outs = []
+                for k, s, t in zip(keys, streams, temps):
+                    ko, vo = torch.empty_like(k), torch.empty_like(vals)
+                    with torch.cuda.stream(s):
+                        rc = b2s.b2s_radix_sort(H._p(t), ctypes.byref(nbytes), H._p(k), H._p(ko), H._p(vals), H._p(vo), n, 6, 4, 4,
+                                                0, 0, 32, ctypes.c_void_p(s.cuda_stream))
+                    assert rc == 0
+                    outs.append((ko, vo))
+                torch.cuda.synchronize()
+                for (ko, vo), (ek, ev) in zip(outs, expect):
+                    assert torch.equal(ko, ek) and torch.equal(vo, ev), f"claim={claim} rep={rep}"
+        finally:
+            b2s.b2s_set_tile_claim(old)

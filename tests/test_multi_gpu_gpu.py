@@ -43,7 +43,8 @@ def test_split_kernels_vs_numpy(b2s, kt, vb):
             cand[0] = raw[3]
         order = np.argsort([mg.sort_key(int(k), kt, desc, bb, eb) for k in cand], kind="stable")
         sp_keys = cand[order]
-        sp_ranks = rng.integers(0, 8, nsp).astype(np.int32)
+        # splitters are (key, source rank) pairs ascending in that order (they come out of a stable sort of the samples)
+        sp_ranks = np.sort(rng.integers(0, 8, nsp)).astype(np.int32)
         rank = 3
         vals = np.arange(n, dtype=H.NP_BITS[vb]) if vb else None
         dk, dv = H.to_dev(raw), (H.to_dev(vals) if vb else None)
@@ -56,6 +57,13 @@ def test_split_kernels_vs_numpy(b2s, kt, vb):
         offs = torch.from_numpy(np.concatenate(([0], np.cumsum(exp_counts)[:-1])).astype(np.int64)).cuda()
         ok, ov = torch.empty_like(dk), (torch.empty_like(dv) if vb else None)
         ops.split_scatter(dk, dv, ok, ov, n, kt, desc, bb, eb, d_sp_keys, d_sp_ranks, rank, offs, None, None, {})
+        # destinations that are only element-aligned take the item-store write-out instead of the bulk copies
+        okm = torch.empty(n + 4, dtype=dk.dtype, device="cuda")
+        ovm = torch.empty(n + 4, dtype=dv.dtype, device="cuda") if vb else None
+        ops.split_scatter(dk, dv, okm[1:], ovm[1:] if vb else None, n, kt, desc, bb, eb, d_sp_keys, d_sp_ranks, rank, offs, None,
+                          None, {})
+        torch.cuda.synchronize()
+        assert torch.equal(okm[1:n + 1], ok) and (not vb or torch.equal(ovm[1:n + 1], ov)), "item-store and bulk write-out differ"
         # PEER write-out path with every "peer" pointing at the local buffer, and the capacity guard
         ok2, ov2 = torch.zeros_like(dk), (torch.zeros_like(dv) if vb else None)
         ops.split_scatter(dk, dv, None, None, n, kt, desc, bb, eb, d_sp_keys, d_sp_ranks, rank, offs, [ok2.data_ptr()] * 8,
@@ -94,18 +102,29 @@ def _worker(rank, world, path, exchange, ret):
                     k = H.random_bits(rng, n_local, 8)
                 shards.append(k.astype(H.NP_BITS[kb]))
                 vals.append(np.arange(n_local, dtype=np.uint32) + np.uint32(10_000_000 * r))
-            sorter = mg.DistributedSorter(n_local, kd, torch.int32, descending=desc, samples_per_rank=1024, slack=1.6,
-                                          exchange=exchange)
+            if exchange == "native":  # the C++ host inside libb2s.so (include/b2s_mgpu.h)
+                sorter = mg.NativeDistributedSorter(n_local, kd, torch.int32, descending=desc, samples_per_rank=1024, slack=1.6)
+            else:
+                sorter = mg.DistributedSorter(n_local, kd, torch.int32, descending=desc, samples_per_rank=1024, slack=1.6,
+                                              exchange=exchange)
             tk = H.to_dev(shards[rank]).view(kd)
             tv = H.to_dev(vals[rank])
-            for _ in range(2):  # twice: buffer reuse across sorts
+            # first a sort whose shard size differs on ONE rank only (sizes may change freely between calls), then the
+            # full shards twice (buffer reuse across sorts)
+            short = n_local - 12_345 if rank == 1 else n_local
+            o1 = sorter.sort(tk[:short], tv[:short])
+            assert sum(o1.counts_all) == n_local * world - 12_345
+            assert sorter.verify(tk[:short], tv[:short], o1, values_are_global_indices=True)
+            for _ in range(2):
                 out = sorter.sort(tk, tv)
-            assert sorter.verify(tk, tv, out)
+            assert sorter.verify(tk, tv, out, values_are_global_indices=True)
             ek, ev = po.radix_sort(np.concatenate(shards), np.concatenate(vals), kt, desc)
             lo = sum(out.counts_all[:rank])
             got_k = out.keys.view(H.CONTAINER[kb]).cpu().numpy().view(H.NP_BITS[kb])
             assert np.array_equal(got_k, ek[lo: lo + out.count]), f"{mode}: keys differ"
             assert np.array_equal(out.values.cpu().numpy().view(np.uint32), ev[lo: lo + out.count]), f"{mode}: values differ"
+            if hasattr(sorter, "close"):
+                sorter.close()
             del sorter
         ret[rank] = "ok"
     except Exception:  # noqa: BLE001
@@ -116,7 +135,7 @@ def _worker(rank, world, path, exchange, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["nccl", "peer", "native"])
 def test_distributed_sorter_nccl(exchange):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:

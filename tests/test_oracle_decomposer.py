@@ -1,5 +1,5 @@
-"""Pins the decomposer (custom struct key) restatement in oracle/pyoracle.py -- the checker for SURVEY.md §8(f)2, which has no
-product counterpart yet -- against the reference's own known-answer vectors
+"""Pins the decomposer (custom struct key) restatement in oracle/pyoracle.py -- the checker for SURVEY.md §8(f)2 (product:
+cub_b200/csrc/b2s_struct.cu, tests/test_struct_gpu.py) -- against the reference's own known-answer vectors
 (test/catch2_test_device_radix_sort_custom.cu:555-1690, extracted by tests/golden/make_decomposer_kats.py), plus two
 properties: a one-field decomposition equals the fundamental-type oracle, and the sort is stable."""
 import json
@@ -37,8 +37,7 @@ def test_single_field_equals_fundamental_oracle():
         vals = np.arange(raw.shape[0], dtype=np.uint32)
         for desc in (False, True):
             for bb, eb in ((0, None), (3, raw.dtype.itemsize * 8 - 2)):
-                if kt in (5, 8, 11) and bb:
-                    continue  # partial bit ranges on floating keys are unpinned in the reference
+                # floating keys with a partial range: both restatements follow the reference's onesweep zero handling
                 perm = po.decomposed_sort_permutation([(raw, kt)], desc, bb, eb)
                 ek, ev = po.radix_sort(raw, vals, kt, desc, bb, eb)
                 assert np.array_equal(raw[perm], ek) and np.array_equal(vals[perm], ev), (kt, desc, bb, eb)
