@@ -515,10 +515,18 @@ int b2s_split_scatter(void* d_temp_storage, size_t* temp_storage_bytes, const vo
   return (int)ks->split(a, s);
 }
 
+// 128-bit integer keys are a two-member composite on this little-endian machine: high word (signed for __int128), low word
+static const b2s_field_t kFieldsU128[2] = {{8, B2S_U64}, {0, B2S_U64}};
+static const b2s_field_t kFieldsI128[2] = {{8, B2S_I64}, {0, B2S_U64}};
+
 int b2s_radix_sort(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, void* d_keys_out,
                    const void* d_values_in, void* d_values_out, uint64_t num_items, int key_type, int value_bytes,
                    int offset_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream) {
   (void)offset_bytes;
+  if (key_type == B2S_U128 || key_type == B2S_I128)
+    return b2s_radix_sort_struct(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, 16,
+                                 key_type == B2S_U128 ? kFieldsU128 : kFieldsI128, 2, value_bytes, descending, begin_bit, end_bit,
+                                 stream);
   void* k[2] = {const_cast<void*>(d_keys_in), d_keys_out};
   void* v[2] = {const_cast<void*>(d_values_in), d_values_out};
   return b2s::sort_impl(d_temp_storage, temp_storage_bytes, k, v, nullptr, false, num_items, key_type, value_bytes,
@@ -529,6 +537,10 @@ int b2s_radix_sort_db(void* d_temp_storage, size_t* temp_storage_bytes, void* ke
                       void* val_bufs[2], int* val_selector, uint64_t num_items, int key_type, int value_bytes,
                       int offset_bytes, int descending, int begin_bit, int end_bit, b2s_stream_t stream) {
   (void)offset_bytes;
+  if (key_type == B2S_U128 || key_type == B2S_I128)
+    return b2s_radix_sort_struct_db(d_temp_storage, temp_storage_bytes, key_bufs, key_selector, val_bufs, val_selector, num_items,
+                                    16, key_type == B2S_U128 ? kFieldsU128 : kFieldsI128, 2, value_bytes, descending, begin_bit,
+                                    end_bit, stream);
   if (!key_bufs || !key_selector) return (int)cudaErrorInvalidValue;
   if (value_bytes && (!val_bufs || !val_selector)) return (int)cudaErrorInvalidValue;
   const int ks = *key_selector & 1;
@@ -604,6 +616,7 @@ int b2s_digit_histogram(const void* d_keys, uint64_t num_items, int key_type, in
 }
 
 int b2s_key_bytes(int key_type) {
+  if (key_type == B2S_U128 || key_type == B2S_I128) return 16;
   return (key_type >= 0 && key_type < B2S_KEY_TYPE_COUNT) ? b2s::kKeyInfo[key_type].bytes : 0;
 }
 

@@ -65,6 +65,10 @@ B200_KEY(long, (sizeof(long) == 8 ? B2S_I64 : B2S_I32));
 B200_KEY(unsigned long long, B2S_U64);
 B200_KEY(long long, B2S_I64);
 B200_KEY(double, B2S_F64);
+#if defined(__SIZEOF_INT128__)
+B200_KEY(__uint128_t, B2S_U128);  // cub/util_type.cuh:1225,1259
+B200_KEY(__int128_t, B2S_I128);
+#endif
 #ifdef B200_HAS_HALF
 B200_KEY(__half, B2S_F16);
 #endif
@@ -79,7 +83,7 @@ constexpr int value_bytes() {
     return 0;
   } else {
     static_assert(sizeof(V) == 1 || sizeof(V) == 2 || sizeof(V) == 4 || sizeof(V) == 8 || sizeof(V) == 16,
-                  "value types of 1, 2, 4, 8 or 16 bytes are supported");
+                  "value types of 1, 2, 4, 8 or 16 bytes are supported (any size up to 64 bytes with struct / 128-bit keys)");
     return (int)sizeof(V);
   }
 }

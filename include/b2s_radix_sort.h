@@ -54,7 +54,12 @@ typedef enum {
   B2S_U64 = 9,
   B2S_I64 = 10,
   B2S_F64 = 11,
-  B2S_KEY_TYPE_COUNT = 12
+  B2S_KEY_TYPE_COUNT = 12,
+  /* 128-bit integer keys (util_type.cuh:1225,1259; test matrix test_device_radix_sort.cu:2238): accepted by
+   * b2s_radix_sort / b2s_radix_sort_db (values of any size up to 64 bytes); sorted as a (high word, low word) composite
+   * through the pack -> SortPairs<u64, index> -> gather path of b2s_radix_sort_struct. */
+  B2S_U128 = 16,
+  B2S_I128 = 17
 } b2s_key_t;
 
 /* cudaStream_t is passed as an opaque pointer so that C callers need no CUDA headers. */
