@@ -65,12 +65,38 @@ def _ptr(x) -> Optional[int]:
     return int(x)
 
 
-def _stream_handle(stream) -> int:
+def _stream_handle(stream, device=None) -> int:
     if stream is None:
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(device).cuda_stream
     if isinstance(stream, torch.cuda.Stream):
         return stream.cuda_stream
     return int(stream)
+
+
+def _device_of(*objs):
+    """The CUDA device the tensors among `objs` live on (None when only raw pointers are given); the C-ABI works on the
+    CURRENT device, so callers run it under ``torch.cuda.device(dev)`` and take the stream from that device.  Tensors on
+    different devices are an error (the kernels would fault or silently go through peer access)."""
+    dev = None
+    for o in objs:
+        if isinstance(o, torch.Tensor) and o.is_cuda:
+            if dev is not None and o.device != dev:
+                raise ValueError(f"all device arrays of one sort must be on one device (got {dev} and {o.device})")
+            dev = o.device
+    return dev
+
+
+class _on_device:
+    def __init__(self, dev):
+        self.ctx = torch.cuda.device(dev) if dev is not None else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def _infer(keys, values, key_type, value_bytes) -> Tuple[int, int]:
@@ -100,10 +126,12 @@ def _call_ptr(descending, d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_
     if end_bit is None:
         end_bit = KEY_BYTES[key_type] * 8
     nbytes = ctypes.c_size_t(int(temp_storage_bytes or 0))
-    err = lib.b2s_radix_sort(_ptr(d_temp_storage), ctypes.byref(nbytes), _ptr(d_keys_in), _ptr(d_keys_out),
-                             _ptr(d_values_in), _ptr(d_values_out), int(num_items), key_type, value_bytes,
-                             _offset_bytes(int(num_items)), int(bool(descending)), int(begin_bit), int(end_bit),
-                             _stream_handle(stream) if d_temp_storage is not None else None)
+    dev = _device_of(d_temp_storage, d_keys_in, d_keys_out, d_values_in, d_values_out)
+    with _on_device(dev):
+        err = lib.b2s_radix_sort(_ptr(d_temp_storage), ctypes.byref(nbytes), _ptr(d_keys_in), _ptr(d_keys_out),
+                                 _ptr(d_values_in), _ptr(d_values_out), int(num_items), key_type, value_bytes,
+                                 _offset_bytes(int(num_items)), int(bool(descending)), int(begin_bit), int(end_bit),
+                                 _stream_handle(stream, dev) if d_temp_storage is not None else None)
     return err, nbytes.value
 
 
@@ -124,10 +152,12 @@ def _call_db(descending, d_temp_storage, temp_storage_bytes, d_keys: DoubleBuffe
     else:
         vsel = ctypes.c_int(0)
         vb_arg, vsel_arg = None, None
-    err = lib.b2s_radix_sort_db(_ptr(d_temp_storage), ctypes.byref(nbytes), kb, ctypes.byref(ksel), vb_arg, vsel_arg,
-                                int(num_items), key_type, value_bytes, _offset_bytes(int(num_items)),
-                                int(bool(descending)), int(begin_bit), int(end_bit),
-                                _stream_handle(stream) if d_temp_storage is not None else None)
+    dev = _device_of(d_temp_storage, *d_keys.d_buffers, *(d_values.d_buffers if d_values is not None else ()))
+    with _on_device(dev):
+        err = lib.b2s_radix_sort_db(_ptr(d_temp_storage), ctypes.byref(nbytes), kb, ctypes.byref(ksel), vb_arg, vsel_arg,
+                                    int(num_items), key_type, value_bytes, _offset_bytes(int(num_items)),
+                                    int(bool(descending)), int(begin_bit), int(end_bit),
+                                    _stream_handle(stream, dev) if d_temp_storage is not None else None)
     if err == CUDA_SUCCESS and d_temp_storage is not None:
         d_keys.selector = ksel.value
         if d_values is not None and value_bytes:
@@ -196,6 +226,48 @@ class DeviceRadixSort:
         return DeviceRadixSort._keys(True, d_temp_storage, temp_storage_bytes, *args, **kw)
 
 
+class DeviceSegmentedRadixSort:
+    """Mirror of ``cub::DeviceSegmentedRadixSort`` (cub/device/device_segmented_radix_sort.cuh), pointer form:
+    ``(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out[, d_values_in, d_values_out], num_items, num_segments,
+    d_begin_offsets, d_end_offsets, begin_bit=0, end_bit=None, stream=None)`` -> ``(cudaError, temp_storage_bytes)``.
+    The offsets are int32 / int64 CUDA tensors (begin and end may be views ``offsets[:-1]`` / ``offsets[1:]``)."""
+
+    @staticmethod
+    def _run(descending, d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items,
+             num_segments, d_begin_offsets, d_end_offsets, begin_bit=0, end_bit=None, stream=None, key_type=None, value_bytes=None):
+        lib = _lib.load()
+        key_type, value_bytes = _infer(d_keys_in, d_values_in, key_type, value_bytes)
+        if end_bit is None:
+            end_bit = KEY_BYTES[key_type] * 8
+        if d_begin_offsets.dtype != d_end_offsets.dtype or d_begin_offsets.dtype not in (torch.int32, torch.int64):
+            raise TypeError("segment offsets must be int32 or int64 CUDA tensors of one dtype")
+        nbytes = ctypes.c_size_t(int(temp_storage_bytes or 0))
+        dev = _device_of(d_temp_storage, d_keys_in, d_keys_out, d_values_in, d_values_out, d_begin_offsets, d_end_offsets)
+        with _on_device(dev):
+            err = lib.b2s_segmented_radix_sort(_ptr(d_temp_storage), ctypes.byref(nbytes), _ptr(d_keys_in), _ptr(d_keys_out),
+                                               _ptr(d_values_in), _ptr(d_values_out), int(num_items), int(num_segments),
+                                               _ptr(d_begin_offsets), _ptr(d_end_offsets), d_begin_offsets.element_size(),
+                                               key_type, value_bytes, int(bool(descending)), int(begin_bit), int(end_bit),
+                                               _stream_handle(stream, dev) if d_temp_storage is not None else None)
+        return err, nbytes.value
+
+    @staticmethod
+    def SortPairs(d_temp_storage, temp_storage_bytes, *args, **kw):
+        return DeviceSegmentedRadixSort._run(False, d_temp_storage, temp_storage_bytes, *args, **kw)
+
+    @staticmethod
+    def SortPairsDescending(d_temp_storage, temp_storage_bytes, *args, **kw):
+        return DeviceSegmentedRadixSort._run(True, d_temp_storage, temp_storage_bytes, *args, **kw)
+
+    @staticmethod
+    def SortKeys(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, *args, **kw):
+        return DeviceSegmentedRadixSort._run(False, d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, None, None, *args, **kw)
+
+    @staticmethod
+    def SortKeysDescending(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, *args, **kw):
+        return DeviceSegmentedRadixSort._run(True, d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, None, None, *args, **kw)
+
+
 class CudaError(RuntimeError):
     pass
 
@@ -222,6 +294,22 @@ def sort_pairs(keys: torch.Tensor, values: Optional[torch.Tensor], descending: b
     temp = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
     err, _ = fn(temp, nbytes, *args, begin_bit=begin_bit, end_bit=end_bit, stream=stream)
     _check(err, "radix sort")
+    return keys_out, values_out
+
+
+def segmented_sort_pairs(keys: torch.Tensor, values: Optional[torch.Tensor], offsets: torch.Tensor, descending: bool = False,
+                         begin_bit: int = 0, end_bit: Optional[int] = None, stream=None):
+    """Convenience wrapper: segment s is [offsets[s], offsets[s + 1]); allocates outputs + temp storage."""
+    n, nseg = keys.numel(), offsets.numel() - 1
+    keys_out = keys.clone()  # items outside every segment keep their input value
+    values_out = values.clone() if values is not None else None
+    fn = DeviceSegmentedRadixSort.SortPairsDescending if descending else DeviceSegmentedRadixSort.SortPairs
+    args = (keys, keys_out, values, values_out, n, nseg, offsets[:-1], offsets[1:])
+    err, nbytes = fn(None, 0, *args, begin_bit=begin_bit, end_bit=end_bit)
+    _check(err, "temp-storage query")
+    temp = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+    err, _ = fn(temp, nbytes, *args, begin_bit=begin_bit, end_bit=end_bit, stream=stream)
+    _check(err, "segmented radix sort")
     return keys_out, values_out
 
 

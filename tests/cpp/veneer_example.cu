@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "b200/device_radix_sort.cuh"
+#include "b200/device_segmented_radix_sort.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %d at %s:%d\n", (int)e_, __FILE__, __LINE__); return 2; } } while (0)
 
@@ -118,6 +119,39 @@ int run_struct(int n) {
   return 0;
 }
 
+// Segmented sort, shaped like the reference's documentation snippet (cub/device/device_segmented_radix_sort.cuh:60-100):
+// d_offsets / d_offsets + 1 as begin / end offsets.
+int run_segmented(int n) {
+  std::vector<int> h_keys(n), h_vals(n), h_offsets;
+  unsigned s = 4242u;
+  for (int i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; h_keys[i] = (int)(s >> 4) - (1 << 27); h_vals[i] = i; }
+  for (int o = 0; o < n; o += 1 + (int)((s = s * 1664525u + 1013904223u) >> 18) % 9000) h_offsets.push_back(o);
+  h_offsets.push_back(n);
+  const int num_segments = (int)h_offsets.size() - 1;
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  for (int g = 0; g < num_segments; ++g)
+    std::stable_sort(order.begin() + h_offsets[g], order.begin() + h_offsets[g + 1], [&](int a, int b) { return h_keys[a] < h_keys[b]; });
+  int *d_keys_in, *d_keys_out, *d_vals_in, *d_vals_out, *d_offsets;
+  CK(cudaMalloc(&d_keys_in, n * sizeof(int))); CK(cudaMalloc(&d_keys_out, n * sizeof(int)));
+  CK(cudaMalloc(&d_vals_in, n * sizeof(int))); CK(cudaMalloc(&d_vals_out, n * sizeof(int)));
+  CK(cudaMalloc(&d_offsets, h_offsets.size() * sizeof(int)));
+  CK(cudaMemcpy(d_keys_in, h_keys.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_vals_in, h_vals.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_offsets, h_offsets.data(), h_offsets.size() * sizeof(int), cudaMemcpyHostToDevice));
+  void* d_temp_storage = nullptr; size_t temp_storage_bytes = 0;
+  CK(b200::DeviceSegmentedRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_vals_in, d_vals_out, n,
+                                              num_segments, d_offsets, d_offsets + 1));
+  CK(cudaMalloc(&d_temp_storage, temp_storage_bytes));
+  CK(b200::DeviceSegmentedRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_vals_in, d_vals_out, n,
+                                              num_segments, d_offsets, d_offsets + 1));
+  std::vector<int> got(n);
+  CK(cudaMemcpy(got.data(), d_vals_out, n * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) if (got[i] != order[i]) { printf("segmented form mismatch at %d\n", i); return 1; }
+  cudaFree(d_temp_storage); cudaFree(d_keys_in); cudaFree(d_keys_out); cudaFree(d_vals_in); cudaFree(d_vals_out); cudaFree(d_offsets);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   int n = argc > 1 ? atoi(argv[1]) : 1000003;
   int rc = 0;
@@ -126,6 +160,7 @@ int main(int argc, char** argv) {
   rc |= run<unsigned long long>(n / 3, false);
   rc |= run<double>(n / 5, true);
   rc |= run_struct(n / 2);
+  rc |= run_segmented(n / 2);
   printf(rc == 0 ? "veneer example: OK\n" : "veneer example: FAILED\n");
   return rc;
 }

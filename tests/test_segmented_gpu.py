@@ -173,3 +173,22 @@ def test_segmented_trivial_cases(b2s):
     assert nbytes.value == 1
     assert b2s.b2s_segmented_radix_sort(None, ctypes.byref(nbytes), H._p(z), H._p(z), None, None, 4, 1, H._p(z), H._p(z), 2, 6, 0, 0, 0, 32,
                                         None) != 0  # offset arrays are 4- or 8-byte integers
+
+
+def test_python_mirror_segmented(b2s, oracle):
+    """cub_b200.DeviceSegmentedRadixSort / segmented_sort_pairs (the Python mirror) on tensors of a non-current device-safe path."""
+    import cub_b200 as cb
+
+    rng = np.random.default_rng(3)
+    n = 50_000
+    raw = H.random_bits(rng, n, 4)
+    offs = np.array([0, 100, 100, 9000, 30_000, n], dtype=np.int64)
+    dk = H.to_dev(raw).view(torch.uint32)
+    dv = H.to_dev(np.arange(n, dtype=np.uint32)).view(torch.uint32)
+    ko, vo = cb.segmented_sort_pairs(dk, dv, torch.from_numpy(offs).cuda(), descending=True)
+    torch.cuda.synchronize()
+    for b, e in zip(offs[:-1], offs[1:]):
+        if e > b:
+            ek, ev = oracle.radix_sort(raw[b:e], np.arange(b, e, dtype=np.uint32), 6, True)
+            assert np.array_equal(H.to_np(ko.view(torch.int32), np.uint32)[b:e], ek)
+            assert np.array_equal(H.to_np(vo.view(torch.int32), np.uint32)[b:e], ev)
