@@ -98,29 +98,37 @@ struct SplitterOp {
   const int* d_ranks;              // DEVICE: source rank of every splitter
   int my_rank;
   int count;
-  W s[MAX_SPLITTERS];              // filled by prepare(): splitters as (ordered >> begin_bit) & range_mask
+  W s[MAX_SPLITTERS];              // filled by prepare(): THRESHOLDS: sort key of splitter j, + 1 when its tie bit is clear
   uint32_t tie;                    // filled by prepare(): bit j = splitter j's source rank <= this rank
 
   __device__ __forceinline__ W sort_key(W k) const { return (W)(base.ordered(k) >> base.bit) & range_mask; }
   // Splitters live in device memory (they come out of a device-side sort of the samples), so that the host never
   // has to wait for them; every thread reads the <= 7 of them once (L2 hits).
+  // "key orders at or after splitter j"  <=>  o > s_j || (o == s_j && tie_j)  <=>  o >= s_j + (tie_j ? 0 : 1): one compare
+  // against a precomputed threshold.  A splitter whose threshold would overflow (largest sort key, tie bit clear) can
+  // never match, nor can any later one (splitters ascend in (key, rank) order): `count` is cut there.
   __device__ __forceinline__ void prepare() {
     tie = 0;
+    int live = count;
 #pragma unroll
     for (int j = 0; j < MAX_SPLITTERS; ++j) {
       s[j] = ~W(0);
       if (j < count) {
-        s[j] = sort_key((W)reinterpret_cast<const KeyU*>(d_keys)[j]);
-        tie |= (d_ranks[j] <= my_rank ? 1u : 0u) << j;
+        const W sj = sort_key((W)reinterpret_cast<const KeyU*>(d_keys)[j]);
+        const bool t = d_ranks[j] <= my_rank;
+        tie |= (t ? 1u : 0u) << j;
+        if (!t && sj == range_mask && j < live) live = j;  // threshold sj + 1 does not exist
+        s[j] = t ? sj : sj + 1;
       }
     }
+    count = live;
   }
   __device__ __forceinline__ uint32_t operator()(W k) const {
     const W o = sort_key(k);
     uint32_t d = 0;
 #pragma unroll
     for (int j = 0; j < MAX_SPLITTERS; ++j)
-      if (j < count) d += (o > s[j] || (o == s[j] && ((tie >> j) & 1u))) ? 1u : 0u;
+      if (j < count) d += (o >= s[j]) ? 1u : 0u;
     return d;
   }
   // ge[j] += "k orders at or after splitter j" (the summands of operator()); monotone in j
@@ -128,7 +136,7 @@ struct SplitterOp {
     const W o = sort_key(k);
 #pragma unroll
     for (int j = 0; j < MAX_SPLITTERS; ++j)
-      if (j < count) ge[j] += (o > s[j] || (o == s[j] && ((tie >> j) & 1u))) ? 1u : 0u;
+      if (j < count) ge[j] += (o >= s[j]) ? 1u : 0u;
   }
 };
 

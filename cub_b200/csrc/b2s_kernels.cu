@@ -340,9 +340,24 @@ cudaError_t segmented_v(const SegmentedArgs& a, cudaStream_t s) {
 
 // ---- multi-GPU partition pass (4- and 8-byte keys; values 0/4/8 bytes) -----------------------
 #if (B2S_K == 4 || B2S_K == 8)
-constexpr int SPLIT_NT = 512;
+// Shapes of the partition pass.  0 (default): two 512-thread CTAs per SM; 1: one 1024-thread CTA per SM with a tile twice as
+// large (runs twice as long: larger bulk copies over NVLink); 2: 512 threads with more items per thread.  B2S_SPLIT_SHAPE
+// selects (read once); the temp-storage size depends on the tile, so the choice is per process.
+struct SplitShape { int nt, ipt, minb; };
 template <int V>
-constexpr int split_ipt() { return tmaw_ipt<V>(SPLIT_NT, 2, scale_ipt<V>(16)); }  // the destination functor is register-hungry
+constexpr SplitShape split_shape(int which) {
+  return which == 1   ? SplitShape{1024, tmaw_ipt<V>(1024, 1, scale_ipt<V>(16)), 1}
+         : which == 2 ? SplitShape{512, tmaw_ipt<V>(512, 2, scale_ipt<V>(20)), 2}
+                      : SplitShape{512, tmaw_ipt<V>(512, 2, scale_ipt<V>(16)), 2};  // the destination functor is register-hungry
+}
+inline int split_shape_choice() {
+  static const int c = [] {
+    const char* e = std::getenv("B2S_SPLIT_SHAPE");
+    const int v = e ? std::atoi(e) : 0;
+    return (v >= 0 && v <= 2) ? v : 0;
+  }();
+  return c;
+}
 
 template <bool F>
 SplitterOp<K, F> make_splitter_op(const SplitArgs& a) {
@@ -360,9 +375,9 @@ SplitterOp<K, F> make_splitter_op(const SplitArgs& a) {
   return op;
 }
 
-template <int V, bool F, bool PEER>
-cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
-  constexpr int IPT = split_ipt<V>();
+template <int V, bool F, bool PEER, int SHAPE>
+cudaError_t split_shape_one(const SplitArgs& a, cudaStream_t s) {
+  constexpr SplitShape sh = split_shape<V>(SHAPE);
   using Op = SplitterOp<K, F>;
   OnesweepParams<K, Op> p;
   fill_params(p, a.pass, make_splitter_op<F>(a));
@@ -371,24 +386,33 @@ cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
     p.peer_vals[i] = a.peer_vals[i];
   }
   p.peer_capacity = a.peer_capacity;
-  const unsigned long long tiles = (a.pass.n + SPLIT_NT * IPT - 1) / (SPLIT_NT * IPT);
+  const unsigned long long tiles = (a.pass.n + sh.nt * sh.ipt - 1) / (sh.nt * sh.ipt);
   constexpr int BASE = PEER ? PF_PEER : 0;
   // With <= 8 destinations the runs of a tile are ~1000 items long: every run leaves the SM as one bulk shared->global
   // (or shared->peer over NVLink) copy when the destinations are 16-byte aligned (`bulk`); item stores otherwise.
   if (a.bulk) {
-    using L = PassSmem<K, V, SPLIT_NT, IPT, true>;
-    auto kern = digit_pass_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 6, BASE | PF_TMAW>;
+    using L = PassSmem<K, V, sh.nt, sh.ipt, true>;
+    auto kern = digit_pass_kernel<K, V, Op, unsigned long long, sh.nt, sh.ipt, sh.minb, 6, BASE | PF_TMAW>;
     cudaError_t e = ensure_smem(kern, L::TOTAL);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
+    kern<<<(unsigned int)tiles, sh.nt, L::TOTAL, s>>>(p);
   } else {
-    using L = PassSmem<K, V, SPLIT_NT, IPT, false>;
-    auto kern = digit_pass_kernel<K, V, Op, unsigned long long, SPLIT_NT, IPT, 2, 6, BASE>;
+    using L = PassSmem<K, V, sh.nt, sh.ipt, false>;
+    auto kern = digit_pass_kernel<K, V, Op, unsigned long long, sh.nt, sh.ipt, sh.minb, 6, BASE>;
     cudaError_t e = ensure_smem(kern, L::TOTAL);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned int)tiles, SPLIT_NT, L::TOTAL, s>>>(p);
+    kern<<<(unsigned int)tiles, sh.nt, L::TOTAL, s>>>(p);
   }
   return cudaGetLastError();
+}
+
+template <int V, bool F, bool PEER>
+cudaError_t split_one(const SplitArgs& a, cudaStream_t s) {
+  switch (split_shape_choice()) {
+    case 1: return split_shape_one<V, F, PEER, 1>(a, s);
+    case 2: return split_shape_one<V, F, PEER, 2>(a, s);
+    default: return split_shape_one<V, F, PEER, 0>(a, s);
+  }
 }
 
 template <int V>
@@ -509,10 +533,11 @@ cudaError_t CAT(split_launch_k, B2S_K)(const SplitArgs& a, cudaStream_t s) {
   }
 }
 int CAT(split_tile_k, B2S_K)(int vbytes) {
+  const int c = split_shape_choice();
   switch (vbytes) {
-    case 0: return SPLIT_NT * split_ipt<0>();
-    case 4: return SPLIT_NT * split_ipt<4>();
-    case 8: return SPLIT_NT * split_ipt<8>();
+    case 0: return split_shape<0>(c).nt * split_shape<0>(c).ipt;
+    case 4: return split_shape<4>(c).nt * split_shape<4>(c).ipt;
+    case 8: return split_shape<8>(c).nt * split_shape<8>(c).ipt;
     default: return 0;
   }
 }
