@@ -23,10 +23,23 @@ b2s = _lib.load()
 from oracle import pyoracle as po  # noqa: E402  (checker/comparator only)
 
 impls = {"b2s": (b2s.b2s_radix_sort, b2s.b2s_radix_sort_db)}
+tuned = None
 for name, which in (("ref_cub_2.2.0", "ref"), ("toolkit_cub", "tk")):
     lib = po.load_gpu_reference(which)
     if lib is not None:
         impls[name] = (lib.sort, lib.sort_db)
+        if which == "ref" and hasattr(lib, "tuned_sort"):
+            tuned = lib.tuned_sort
+
+# "best-known CUB on B200": the reference's dispatch with NVIDIA's B200 tuning points injected through SelectedPolicy
+# (oracle/ref_shim_ext.cu, dispatch_radix_sort.cuh:1173): (key type, value bytes) -> shim selector
+TUNED = {(6, 4): 0, (9, 4): 1, (6, 0): 2, (8, 0): 3}
+
+
+def tuned_fn(which):
+    def fn(tmp, nbytes, kin, kout, vin, vout, n, kt, vb, ob, desc, bb, eb, stream):
+        return tuned(tmp, nbytes, kin, kout, vin, vout, n, which, bb, eb, stream)
+    return fn
 try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:  # noqa: BLE001
@@ -37,8 +50,10 @@ CONFIGS = [
     ("c1 SortKeys u32 2^24 uniform", 6, 0, 24, 1, False, 0, 32, False, "ptr"),
     ("c2 SortPairs u32/u32 2^28 uniform", 6, 4, 28, 1, False, 0, 32, False, "ptr"),
     ("c2e SortPairs u32/u32 2^28 AND-of-3", 6, 4, 28, 3, False, 0, 32, False, "ptr"),
+    ("c3s SortPairs u64/u32 2^28 uniform (tuned-CUB comparator size)", 9, 4, 28, 1, False, 0, 64, False, "ptr"),
     ("c3 SortPairs u64/u32 2^30 AND-of-3 bits[1,63)", 9, 4, 30, 3, False, 1, 63, False, "db"),
     ("c3b SortPairs u64/u32 2^30 AND-of-3 bits[24,56)", 9, 4, 30, 3, False, 24, 56, False, "db"),
+    ("c4a SortKeys f32 2^28 ascending (tuned-CUB comparator)", 8, 0, 28, 1, False, 0, 32, True, "ptr"),
     ("c4 SortKeysDescending f32 2^29 (NaN, +-0, denormals)", 8, 0, 29, 1, True, 0, 32, True, "ptr"),
     ("c4b SortKeysDescending bf16 2^29", 5, 0, 29, 1, True, 0, 16, True, "ptr"),
 ]
@@ -103,10 +118,13 @@ with open(a.out, "a") as out:
         passes = (eb - bb + 7) // 8
         bytes_per_key = kbytes + passes * 2 * (kbytes + vb)
         golden = None
-        for name in ("ref_cub_2.2.0", "toolkit_cub", "b2s"):
-            if name not in impls:
+        run = dict(impls)
+        if tuned is not None and (kt, vb) in TUNED and not desc and form == "ptr" and n < (1 << 31):
+            run["ref_cub_2.2.0_b200_tuned"] = (tuned_fn(TUNED[(kt, vb)]), None)
+        for name in ("ref_cub_2.2.0", "ref_cub_2.2.0_b200_tuned", "toolkit_cub", "b2s"):
+            if name not in run:
                 continue
-            ms, ko, vo = time_one(impls[name], keys, vals, kt, desc, bb, eb, form)
+            ms, ko, vo = time_one(run[name], keys, vals, kt, desc, bb, eb, form)
             exact = None
             if name == "ref_cub_2.2.0":
                 golden = (ko.clone(), vo.clone() if vo is not None else None)

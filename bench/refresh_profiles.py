@@ -13,6 +13,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+PFX = sys.argv[2] if len(sys.argv) > 2 else tag[:2]  # file-name prefix under profiles/ (r1, r2, ...)
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
@@ -33,21 +34,21 @@ def metric(txt, name):
 
 n = 1 << 28
 traffic = {}
-t = summary(os.path.join(G, f"prof_onesweep_{tag}.ncu-rep"), os.path.join(P, "r1_onesweep_production.ncu.txt"), n // 32)
+t = summary(os.path.join(G, f"prof_onesweep_{tag}.ncu-rep"), os.path.join(P, f"{PFX}_digit_pass_production.ncu.txt"), n // 32)
 name = re.search(r"Kernel Name = (.*)", t).group(1).strip()
 rd, wr = metric(t, "dram__bytes_read.sum"), metric(t, "dram__bytes_write.sum")
 traffic["onesweep_kernel_u32_u32_2p28"] = {
     "dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
     "algorithmic_bytes_per_launch": n * 16,
-    "source": f"profiles/r1_onesweep_production.ncu.txt (ncu --set full --clock-control none, one launch of {name}, n = 2^28)"}
-t = summary(os.path.join(G, f"prof_onesweep_keys_{tag}.ncu-rep"), os.path.join(P, "r1_onesweep_production_keys_only.ncu.txt"), n // 32)
+    "source": f"profiles/{PFX}_digit_pass_production.ncu.txt (ncu --set full --clock-control none, one launch of {name}, n = 2^28)"}
+t = summary(os.path.join(G, f"prof_onesweep_keys_{tag}.ncu-rep"), os.path.join(P, f"{PFX}_digit_pass_production_keys_only.ncu.txt"), n // 32)
 traffic["onesweep_kernel_u32_keys_2p28"] = {
     "dram_bytes_per_launch": int(metric(t, "dram__bytes_read.sum") + metric(t, "dram__bytes_write.sum")),
-    "algorithmic_bytes_per_launch": n * 8, "source": "profiles/r1_onesweep_production_keys_only.ncu.txt"}
-t = summary(os.path.join(G, f"prof_hist_{tag}.ncu-rep"), os.path.join(P, "r1_histogram_production.ncu.txt"), n // 32)
+    "algorithmic_bytes_per_launch": n * 8, "source": f"profiles/{PFX}_digit_pass_production_keys_only.ncu.txt"}
+t = summary(os.path.join(G, f"prof_hist_{tag}.ncu-rep"), os.path.join(P, f"{PFX}_histogram_production.ncu.txt"), n // 32)
 traffic["histogram_kernel_u32_2p28"] = {
     "dram_bytes_per_launch": int(metric(t, "dram__bytes_read.sum") + metric(t, "dram__bytes_write.sum")),
-    "algorithmic_bytes_per_launch": n * 4, "source": "profiles/r1_histogram_production.ncu.txt"}
+    "algorithmic_bytes_per_launch": n * 4, "source": f"profiles/{PFX}_histogram_production.ncu.txt"}
 json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 
 # launch list of the bench command
@@ -66,21 +67,22 @@ for r in rows[1:]:
     agg[k][0] += 1
     agg[k][1] += v
 tot = sum(v[1] for v in agg.values())
-with open(os.path.join(P, "r1_launches_bench.txt"), "w") as f:
+with open(os.path.join(P, f"{PFX}_launches_bench.txt"), "w") as f:
     f.write("ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3   "
             "(per-launch times are cold-cache/serialised: compare shares)\n")
     f.write("The bench command also times reference CUB 2.2.0 (DeviceRadixSortPolicy) and toolkit CUB (policy_hub) on the same input.\n")
     f.write(f"{'kernel':92s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}\n")
     for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k[:90]:92s} {c:8d} {us:12.1f} {us / c:10.1f} {100 * us / tot:6.1f}%\n")
-    ours = {k: v for k, v in agg.items() if k.startswith("onesweep_kernel") or k.startswith("histogram_kernel")}
+    ours = {k: v for k, v in agg.items() if k.startswith("digit_pass_kernel") or k.startswith("onesweep_kernel") or k.startswith("histogram_kernel")}
     ot = sum(v[1] for v in ours.values())
     h = sum(v[1] for k, v in ours.items() if k.startswith("histogram"))
-    f.write(f"\nshares inside our sort: histogram_kernel {100 * h / ot:.1f}%, onesweep_kernel {100 * (ot - h) / ot:.1f}%\n")
+    f.write(f"\nshares inside our sort: histogram_kernel {100 * h / ot:.1f}%, digit_pass_kernel {100 * (ot - h) / ot:.1f}%\n")
 
-shutil.copy(os.path.join(G, f"bench_{tag}.json"), os.path.join(P, "r1_bench_n1.json"))
-shutil.copy(os.path.join(G, f"bench_ref_{tag}.json"), os.path.join(P, "r1_bench_reference_arm.json"))
-shutil.copy(os.path.join(G, f"configs_{tag}.jsonl"), os.path.join(P, "r1_configs_vs_reference.jsonl"))
+for src, dst in ((f"bench_{tag}.json", f"{PFX}_bench_n1.json"), (f"bench_ref_{tag}.json", f"{PFX}_bench_reference_arm_n1.json"),
+                 (f"configs_{tag}.jsonl", f"{PFX}_configs_vs_reference.jsonl")):
+    if os.path.exists(os.path.join(G, src)):
+        shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
 # SASS listings of the production kernels
 def sass(obj, pattern, out):
@@ -92,6 +94,12 @@ def sass(obj, pattern, out):
     return syms[0]
 
 B = os.path.join(ROOT, "cub_b200", "csrc", "build")
-print(sass(os.path.join(B, "k4.o"), r"onesweep_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEjLi", os.path.join(P, "r1_onesweep_u32_u32.sass")))
-print(sass(os.path.join(B, "k4.o"), r"histogram_kernelILi4ELb0EjLb1", os.path.join(P, "r1_histogram_u32.sass")))
-print(open(os.path.join(P, "r1_launches_bench.txt")).read())
+print(sass(os.path.join(B, "k4.o"), r"digit_pass_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEjLi448ELi24ELi2ELi8ELi1E", os.path.join(P, f"{PFX}_digit_pass_u32_u32.sass")))
+print(sass(os.path.join(B, "k4.o"), r"histogram_kernelILi4ELb0EjLb1", os.path.join(P, f"{PFX}_histogram_u32.sass")))
+print(open(os.path.join(P, f"{PFX}_launches_bench.txt")).read())
+
+for rep, out in ((f"prof_onesweep_{tag}.ncu-rep", f"{PFX}_digit_pass_production_by_line.txt"),
+                 (f"prof_onesweep_keys_{tag}.ncu-rep", f"{PFX}_digit_pass_production_keys_only_by_line.txt")):
+    txt = subprocess.run([sys.executable, os.path.join(ROOT, "bench", "ncu_by_line.py"), os.path.join(G, rep), str(n // 32)],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(P, out), "w").write(txt)

@@ -88,6 +88,11 @@ bool g_claim = [] {
   const char* e = std::getenv("B2S_TILE_CLAIM");
   return e && e[0] == '1';
 }();
+// B2S_SKIP_CONSTANT=0 disables the constant-digit short circuit (A/B runs): every pass then ranks and scatters
+bool g_skip_constant = [] {
+  const char* e = std::getenv("B2S_SKIP_CONSTANT");
+  return !(e && e[0] == '0');
+}();
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;
@@ -146,7 +151,7 @@ Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off6
   const size_t osz = off64 ? 8 : 4;
   const uint64_t tiles = (n + tile - 1) / tile;
   size_t o = 0;
-  L.off_ctrs = o;      o += align_up(sizeof(unsigned int) * (size_t)(1 + passes), 256);
+  L.off_ctrs = o;      o += align_up(sizeof(unsigned int) * (size_t)(1 + 2 * passes), 256);  // ticket, tile counters, pass flags
   L.off_hist = o;      o += align_up(osz * 256 * (size_t)passes, 256);
   L.off_status0 = o;   o += align_up(osz * 256 * tiles, 256);
   L.zero_bytes = o;
@@ -255,6 +260,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   h.num_passes = passes;
   h.ghist = hist;
   h.done = ctrs;
+  h.flags = g_skip_constant ? ctrs + 1 + passes : nullptr;
   h.off64 = off64;
   {
     const uint64_t vecs = (n * kbytes + 16 * 1024 - 1) / (16 * 1024);  // CTAs worth of 128-bit loads
@@ -302,6 +308,7 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     a.vbytes = vbytes;
     a.trace = (g_trace_pass == p) ? g_trace : nullptr;
     a.claim = g_claim;
+    a.skip_flag = g_skip_constant ? ctrs + 1 + passes + p : nullptr;
     e = ks->onesweep(variant, a, stream);
     if (e != cudaSuccess) return (int)e;
     g_last_launches++;
@@ -607,6 +614,7 @@ int b2s_digit_histogram(const void* d_keys, uint64_t num_items, int key_type, in
   h.num_passes = passes;
   h.ghist = d_offsets;
   h.done = reinterpret_cast<unsigned int*>(d_offsets + (size_t)passes * 256);
+  h.flags = nullptr;
   h.off64 = true;
   const uint64_t vecs = (num_items * ki.bytes + 16 * 1024 - 1) / (16 * 1024);
   uint64_t g = (uint64_t)b2s::sm_count();

@@ -38,6 +38,7 @@ struct HistParams {
   int num_passes;
   void* ghist;          // OffT[num_passes][256]: counts, then exclusive offsets
   unsigned int* done;   // CTA completion ticket
+  unsigned int* flags;  // [num_passes], zero on entry (may be null): flags[p] = 1 when ONE digit of pass p holds all n keys
 };
 
 // FULL: begin_bit == 0 and end_bit == key bits (the default arguments): every digit is a whole byte at a constant
@@ -152,6 +153,9 @@ __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const HistParam
     const int i = base_i + tid;
     const bool active = i < total;
     const OffT c = active ? __ldcg(&ghist[i]) : OffT(0);
+    // a pass whose digit is the same for every key moves nothing: the digit pass turns into a plain copy (the reference's
+    // single-bin short circuit, cub/agent/agent_radix_sort_onesweep.cuh:344-420, decided once per pass instead of per tile)
+    if (active && P.flags && (unsigned long long)c == P.n) P.flags[i >> RADIX_BITS] = 1u;
     OffT incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

@@ -22,6 +22,7 @@ struct HistArgs {
   int begin_bit, end_bit, num_passes;
   void* ghist;
   unsigned int* done;
+  unsigned int* flags;  // [num_passes] constant-digit flags (zeroed by the caller), may be null
   bool off64;
   int grid;
 };
@@ -43,6 +44,7 @@ struct PassArgs {
   int vbytes;
   unsigned long long* trace;  // tuning builds: per-tile phase timestamps (u64[tiles][16]) of one selected pass, else null
   bool claim;                 // tile ids from an atomic ticket instead of the block index (see b2s_set_tile_claim)
+  const unsigned int* skip_flag;  // DEVICE flag written by the histogram kernel: non-zero = every key has the same digit in this pass
 };
 
 // Whole sort of one small tile in a single launch (b2s_single_tile.cuh).

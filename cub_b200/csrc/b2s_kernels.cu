@@ -173,6 +173,7 @@ void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
   p.pad_key = a.dc.pad_key;
   p.ones = 0xffffffffu;
   p.trace = a.trace;
+  p.skip_flag = a.skip_flag;
   p.op = op;
   for (int i = 0; i < MAX_PEERS; ++i) p.peer_keys[i] = p.peer_vals[i] = nullptr;
   p.peer_capacity = ~0ull;
@@ -259,6 +260,7 @@ cudaError_t hist_one(const HistArgs& a, cudaStream_t s) {
   p.num_passes = a.num_passes;
   p.ghist = a.ghist;
   p.done = a.done;
+  p.flags = a.flags;
   const bool full = a.begin_bit == 0 && a.end_bit == K * 8;
   auto kern = full ? histogram_kernel<K, F, OffT, true> : histogram_kernel<K, F, OffT, false>;
   cudaError_t e = ensure_smem(kern, HistSmem<K>::BYTES);

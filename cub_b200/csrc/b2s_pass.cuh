@@ -57,6 +57,7 @@ struct OnesweepParams {
   unsigned long long n;
   unsigned long long pad_key;  // raw key whose bit-ordered form is all ones
   unsigned long long* trace;   // tuning builds only (b2s_onesweep.cuh); unused here
+  const unsigned int* skip_flag;  // DEVICE (may be null): non-zero = one digit holds every key of this pass -> the pass is a copy
   unsigned int ones;           // 0xffffffff, as a launch parameter so that the compiler cannot fold it (see agree_bit)
   OpT op;              // key -> digit of this pass (DigitOp), or key -> destination rank (SplitterOp)
   void* peer_keys[MAX_PEERS];
@@ -281,6 +282,31 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
     }
     __syncthreads();
   }
+  }
+
+  // ---- constant-digit pass (flag from the upfront histogram): the stable partition is the identity -- copy the staged
+  // tile to the same positions of the output and leave.  (The reference short-circuits single-bin TILES,
+  // cub/agent/agent_radix_sort_onesweep.cuh:344-420; here the upfront histogram already knows it for the whole pass.)
+  if (P.skip_flag != nullptr && __ldg(P.skip_flag) != 0u) {
+    const unsigned long long tile = tile_now();
+    const TileGeom g = geom(tile);
+    const int valid = g.full ? TILE : (int)g.remain;
+    if (tid < RADIX && P.status_next) reinterpret_cast<OffT*>(P.status_next)[tile * RADIX + tid] = 0;
+    if (g.bulk) {
+      mbar_wait(&bar[0], 0);
+      if (HAS_VALUES) mbar_wait(&bar[1], 0);
+    }
+    const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + (g.bulk ? g.kshift : 0u));
+    KeyU* ok = reinterpret_cast<KeyU*>(P.keys_out) + g.base;
+#pragma unroll 4
+    for (int i = tid; i < valid; i += NT) ok[i] = sk[i];
+    if (HAS_VALUES) {
+      const ValU* sv = reinterpret_cast<const ValU*>(stage_v + (g.bulk ? g.vshift : 0u));
+      ValU* ov = reinterpret_cast<ValU*>(P.vals_out) + g.base;
+#pragma unroll 4
+      for (int i = tid; i < valid; i += NT) ov[i] = sv[i];
+    }
+    return;
   }
 
   // ---- P1: keys -> registers (warp-striped rows); counting sweep

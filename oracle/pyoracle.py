@@ -137,6 +137,11 @@ def load_gpu_reference(which: str = "ref"):
         lib.segmented_sort.restype = c.c_int
         lib.segmented_sort.argtypes = [c.c_void_p, c.POINTER(c.c_size_t), c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64,
                                        c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
+        if hasattr(lib, prefix + "_tuned_sort"):
+            lib.tuned_sort = getattr(lib, prefix + "_tuned_sort")
+            lib.tuned_sort.restype = c.c_int
+            lib.tuned_sort.argtypes = [c.c_void_p, c.POINTER(c.c_size_t), c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64,
+                                       c.c_int, c.c_int, c.c_int, c.c_void_p]
         lib.sort128 = getattr(lib, prefix + "_sort128")
         lib.sort128.restype = c.c_int
         lib.sort128.argtypes = [c.c_void_p, c.POINTER(c.c_size_t), c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64,

@@ -115,3 +115,56 @@ extern "C" int CAT(REF_PREFIX, _sort128)(void* tmp, size_t* bytes, const void* k
   return -2;
 #endif
 }
+
+// ---- "best-known CUB on B200": the reference's own dispatch with NVIDIA's B200 tuning points injected through its
+// SelectedPolicy hook (cub/device/dispatch/dispatch_radix_sort.cuh:1173), the way benchmarks/bench/radix_sort/pairs.cu:42-92
+// builds its tuning variants.  Points (threads x items per thread) from the CUDA 12.9 toolkit's
+// cub/device/dispatch/tuning/tuning_radix_sort.cuh (unused by that release's selector): u32/u32 pairs 448 x 20,
+// u64/u32 pairs 352 x 12, u32 keys 512 x 21, f32 keys 512 x 20.  Speed comparator only (results equal the stock build's).
+namespace {
+template <typename KeyT, typename ValueT, typename OffsetT, int THREADS, int ITEMS>
+struct tuned_policy_hub {
+  using DominantT = rc::detail::conditional_t<(sizeof(ValueT) > sizeof(KeyT)), ValueT, KeyT>;
+  struct policy_t : rc::ChainedPolicy<300, policy_t, policy_t> {
+    static constexpr int ONESWEEP_RADIX_BITS = 8;
+    static constexpr bool ONESWEEP = true;
+    static constexpr bool OFFSET_64BIT = sizeof(OffsetT) == 8;
+    using OnesweepPolicy = rc::AgentRadixSortOnesweepPolicy<THREADS, ITEMS, DominantT, 1, rc::RADIX_RANK_MATCH_EARLY_COUNTS_ANY,
+                                                            rc::BLOCK_SCAN_RAKING_MEMOIZE, rc::RADIX_SORT_STORE_DIRECT,
+                                                            ONESWEEP_RADIX_BITS>;
+    using HistogramPolicy = rc::AgentRadixSortHistogramPolicy<128, 16, 1, KeyT, ONESWEEP_RADIX_BITS>;
+    using ExclusiveSumPolicy = rc::AgentRadixSortExclusiveSumPolicy<256, ONESWEEP_RADIX_BITS>;
+    using ScanPolicy = rc::AgentScanPolicy<512, 23, OffsetT, rc::BLOCK_LOAD_WARP_TRANSPOSE, rc::LOAD_DEFAULT,
+                                           rc::BLOCK_STORE_WARP_TRANSPOSE, rc::BLOCK_SCAN_RAKING_MEMOIZE>;
+    static constexpr int SINGLE_TILE_RADIX_BITS = (sizeof(KeyT) > 1) ? 6 : 5;
+    using SingleTilePolicy = rc::AgentRadixSortDownsweepPolicy<256, 19, DominantT, rc::BLOCK_LOAD_DIRECT, rc::LOAD_LDG,
+                                                               rc::RADIX_RANK_MEMOIZE, rc::BLOCK_SCAN_WARP_SCANS,
+                                                               SINGLE_TILE_RADIX_BITS>;
+  };
+  using MaxPolicy = policy_t;
+};
+
+template <typename KeyT, typename ValueT, int THREADS, int ITEMS>
+int tuned_sort(void* tmp, size_t* bytes, const void* kin, void* kout, const void* vin, void* vout, uint64_t n, int bb, int eb,
+               cudaStream_t s) {
+  using OffsetT = int;
+  rc::DoubleBuffer<KeyT> dk(const_cast<KeyT*>((const KeyT*)kin), (KeyT*)kout);
+  rc::DoubleBuffer<ValueT> dv(const_cast<ValueT*>((const ValueT*)vin), (ValueT*)vout);
+  using Dispatch = rc::DispatchRadixSort<false, KeyT, ValueT, OffsetT, tuned_policy_hub<KeyT, ValueT, OffsetT, THREADS, ITEMS>>;
+  return (int)Dispatch::Dispatch(tmp, *bytes, dk, dv, (OffsetT)n, bb, eb, /*is_overwrite_okay=*/false, s);
+}
+}  // namespace
+
+// which: 0 = u32/u32 pairs (448 x 20), 1 = u64/u32 pairs (352 x 12), 2 = u32 keys (512 x 21), 3 = f32 keys (512 x 20);
+// pointer form, ascending, n < 2^31
+extern "C" int CAT(REF_PREFIX, _tuned_sort)(void* tmp, size_t* bytes, const void* kin, void* kout, const void* vin, void* vout,
+                                            uint64_t n, int which, int bb, int eb, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (which) {
+    case 0: return tuned_sort<uint32_t, uint32_t, 448, 20>(tmp, bytes, kin, kout, vin, vout, n, bb, eb, s);
+    case 1: return tuned_sort<unsigned long long, uint32_t, 352, 12>(tmp, bytes, kin, kout, vin, vout, n, bb, eb, s);
+    case 2: return tuned_sort<uint32_t, rc::NullType, 512, 21>(tmp, bytes, kin, kout, nullptr, nullptr, n, bb, eb, s);
+    case 3: return tuned_sort<float, rc::NullType, 512, 20>(tmp, bytes, kin, kout, nullptr, nullptr, n, bb, eb, s);
+    default: return -1;
+  }
+}

@@ -530,3 +530,38 @@ def test_lookback_forward_progress_under_concurrency(b2s, refcub):
                     assert torch.equal(ko, ek) and torch.equal(vo, ev), f"claim={claim} rep={rep}"
         finally:
             b2s.b2s_set_tile_claim(old)
+
+
+@pytest.mark.parametrize("kt,vb", [(6, 4), (7, 0), (9, 4), (8, 4), (10, 8), (2, 0)])
+def test_constant_digit_passes_are_copies(b2s, refcub, kt, vb):
+    """Keys whose upper (or lower, or all) digits are the same for every key: those passes run as plain copies (flag from the
+    upfront histogram; the reference's single-bin short circuit, agent_radix_sort_onesweep.cuh:344-420).  Results must stay
+    bit-exact against the reference -- pointer and DoubleBuffer forms, sizes with a partial last tile, unaligned pointers."""
+    nb = H.KEY_BYTES[kt]
+    bits = nb * 8
+    for n, mask_lo, mask_hi in (((1 << 20) + 12345, 0, bits // 2), (300_007, bits // 4, bits), (70_001, 0, 0), (200_000, 8, bits - 8)):
+        keys = H.gen_device_keys(b2s, n + 8, nb, seed=77)
+        # keep only bits [mask_lo, mask_hi) random; everything else constant (also non-zero constants)
+        width = mask_hi - mask_lo
+        m = ((1 << width) - 1) << mask_lo if width > 0 else 0
+        const = 0x5A5A5A5A5A5A5A5A & ((1 << bits) - 1) & ~m
+        if m >= 1 << (bits - 1):
+            m -= 1 << bits
+        if const >= 1 << (bits - 1):
+            const -= 1 << bits
+        keys = (keys & m) | const
+        vals = H.gen_device_iota(b2s, n + 8, vb) if vb else None
+        for off in (0, 1):
+            k_in = keys[off:off + n]
+            v_in = vals[off:off + n] if vb else None
+            for desc in (False, True):
+                k_ref, v_ref = H.sort_ptr(refcub.sort, k_in, v_in, kt, desc)
+                k_us, v_us = H.sort_ptr(b2s.b2s_radix_sort, k_in, v_in, kt, desc)
+                assert torch.equal(k_us, k_ref), f"keys: kt={kt} n={n} bits[{mask_lo},{mask_hi}) desc={desc} off={off}"
+                if vb:
+                    assert torch.equal(v_us, v_ref), f"values: kt={kt} n={n} bits[{mask_lo},{mask_hi}) desc={desc} off={off}"
+        kb = [keys[:n].clone(), torch.empty_like(keys[:n])]
+        vbuf = [vals[:n].clone(), torch.empty_like(vals[:n])] if vb else None
+        ks, vs = H.sort_db(b2s.b2s_radix_sort_db, kb, vbuf, kt)
+        k_ref, v_ref = H.sort_ptr(refcub.sort, keys[:n], vals[:n] if vb else None, kt)
+        assert torch.equal(kb[ks], k_ref) and (not vb or torch.equal(vbuf[vs], v_ref))
