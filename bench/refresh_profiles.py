@@ -19,8 +19,16 @@ P = os.path.join(ROOT, "profiles")
 
 
 def summary(rep, out, divisor):
-    txt = subprocess.run([sys.executable, os.path.join(ROOT, "bench", "ncu_summary.py"), rep, str(divisor)],
-                         capture_output=True, text=True).stdout
+    # bench/runs/r2l.sh extracts the summaries ON the GPU box (the reports are too large to bring back): use them when the
+    # report itself is absent
+    pre = {"prof_onesweep_": "prof_pass_pairs_", "prof_onesweep_keys_": "prof_pass_keys_", "prof_hist_": "prof_hist_"}
+    base = os.path.basename(rep)[:-len(tag) - len(".ncu-rep")]
+    txtfile = os.path.join(G, pre[base] + tag + ".ncu.txt")
+    if not os.path.exists(rep) and os.path.exists(txtfile):
+        txt = open(txtfile).read()
+    else:
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "bench", "ncu_summary.py"), rep, str(divisor)],
+                             capture_output=True, text=True).stdout
     open(out, "w").write(txt)
     return txt
 
@@ -100,6 +108,11 @@ print(open(os.path.join(P, f"{PFX}_launches_bench.txt")).read())
 
 for rep, out in ((f"prof_onesweep_{tag}.ncu-rep", f"{PFX}_digit_pass_production_by_line.txt"),
                  (f"prof_onesweep_keys_{tag}.ncu-rep", f"{PFX}_digit_pass_production_keys_only_by_line.txt")):
-    txt = subprocess.run([sys.executable, os.path.join(ROOT, "bench", "ncu_by_line.py"), os.path.join(G, rep), str(n // 32)],
-                         capture_output=True, text=True).stdout
+    pre = os.path.join(G, rep.replace("prof_onesweep_keys_", "prof_pass_keys_").replace("prof_onesweep_", "prof_pass_pairs_")
+                       .replace(".ncu-rep", ".by_line.txt"))
+    if not os.path.exists(os.path.join(G, rep)) and os.path.exists(pre):
+        txt = open(pre).read()
+    else:
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "bench", "ncu_by_line.py"), os.path.join(G, rep), str(n // 32)],
+                             capture_output=True, text=True).stdout
     open(os.path.join(P, out), "w").write(txt)

@@ -30,7 +30,7 @@ constexpr int K = B2S_K;
 // laboratory kernel (b2s_onesweep.cuh).  Table entries give items/thread for 4-byte keys with <=4-byte values; wider
 // items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 40;
+constexpr int NUM_VARIANTS = 52;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -69,8 +69,9 @@ constexpr Variant variant_cfg(int vi) {
   const bool pair44 = K == 4 && V == 4;
   const Variant d = V == 0                  ? Variant{384, scale_ipt<V>(F ? 22 : (K <= 4 ? 26 : 24)), 3, 12, 0, 0, 0}
                     : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, 0, 0}
-                    : pair44                ? Variant{448, (F ? 22 : 24) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR}  // (key, value) as one 64-bit store
+                    : pair44                ? Variant{256, (F ? 42 : 46) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR}  // (key, value) as one 64-bit store
                     : (small_pairs && !F)   ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0}
+                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(F ? 40 : 44) - (OFF64 ? 2 : 0), 2, 8, 0, 0, 0}  // wide pairs: few threads, many items each
                                             : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, 0, 0};
 #ifdef B2S_TUNING
   constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);  // lab kernel: the round-1 production flow
@@ -97,6 +98,19 @@ constexpr Variant variant_cfg(int vi) {
     case 15: return Variant{384, scale_ipt<V>(22), 3, 12, 0, 0, 0};
     case 16: return Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0};
     case 17: return Variant{256, scale_ipt<V>(26), 4, 12, 0, 0, 0};
+    // more CTAs per SM with the same per-thread shape (overlap of the latency phases: TMA wait, digit scan, look-back)
+    case 18: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_PAIR};
+    case 19: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_PAIR};
+    case 20: return Variant{288, scale_ipt<V>(40), 2, 8, 0, 0, PF_PAIR};
+    case 21: return Variant{256, scale_ipt<V>(28), 3, 8, 0, 0, PF_PAIR};
+    case 22: return Variant{288, scale_ipt<V>(42), 2, 8, 0, 0, PF_PAIR};
+    case 23: return Variant{320, scale_ipt<V>(34), 2, 8, 0, 0, PF_PAIR};
+    case 24: return Variant{256, scale_ipt<V>(44), 2, 12, 0, 0, PF_PAIR};
+    case 25: return Variant{288, scale_ipt<V>(26), 4, 12, 0, 0, 0};
+    case 26: return Variant{256, scale_ipt<V>(28), 4, 12, 0, 0, 0};
+    case 27: return Variant{320, scale_ipt<V>(30), 3, 12, 0, 0, 0};
+    case 28: return Variant{384, scale_ipt<V>(28), 3, 12, 0, 0, 0};
+    case 29: return Variant{512, scale_ipt<V>(28), 2, 12, 0, 0, 0};
     // laboratory kernel (round 1): production flow, classic flow, the ladder, traces
     case 30: return small_pairs && !F ? Variant{512, scale_ipt<V>(22), 2, 12, 0, M, -1}
                                       : Variant{384, scale_ipt<V>(V == 0 ? (F ? 22 : 24) : (K + V <= 6 && V >= 2) ? (F ? 22 : 24) : (F ? 18 : 20)), 3, 12, 0, M, -1};
@@ -110,6 +124,19 @@ constexpr Variant variant_cfg(int vi) {
     case 37: return Variant{512, scale_ipt<V>(20), 2, 4, 2, 0, -1};
     case 38: return Variant{512, scale_ipt<V>(20), 2, 4, 4, 0, -1};
     case 39: return Variant{512, scale_ipt<V>(20), 2, 4, 8, 0, -1};
+    // round 2, second shape sweep around 256 x 28 x 3 (pairs) -- fewer threads, more items per thread
+    case 40: return Variant{256, scale_ipt<V>(28), 3, 12, 0, 0, PF_PAIR};
+    case 41: return Variant{256, scale_ipt<V>(28), 3, 6, 0, 0, PF_PAIR};
+    case 42: return Variant{256, scale_ipt<V>(26), 3, 8, 0, 0, PF_PAIR};
+    case 43: return Variant{256, scale_ipt<V>(44), 2, 6, 0, 0, PF_PAIR};
+    case 44: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR};
+    case 45: return Variant{384, scale_ipt<V>(28), 2, 8, 0, 0, PF_PAIR};
+    case 46: return Variant{256, scale_ipt<V>(42), 2, 8, 0, 0, PF_PAIR};
+    case 47: return Variant{256, scale_ipt<V>(44), 2, 8, 148, 0, PF_PAIR};
+    case 50: return Variant{256, scale_ipt<V>(44), 2, 8, 296, 0, PF_PAIR};
+    case 51: return Variant{256, scale_ipt<V>(36), 3, 12, 0, 0, 0};
+    case 48: return Variant{256, scale_ipt<V>(32), 3, 12, 0, 0, 0};
+    case 49: return Variant{256, scale_ipt<V>(40), 2, 12, 0, 0, 0};
     default: return d;
   }
 #else
@@ -211,7 +238,7 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
       return cudaGetLastError();
     };
 #ifdef B2S_TUNING
-    return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL>);
+    return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL, (c.abl > 0 ? c.abl : 222)>);  // abl = L2 prefetch distance
 #else
     // ticketed tile ids on request (b2s_set_tile_claim / B2S_TILE_CLAIM=1): no reliance on in-order CTA dispatch
     if (a.claim) return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL | PF_CLAIM>);
