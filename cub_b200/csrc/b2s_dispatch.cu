@@ -12,6 +12,7 @@
 // a sort of P digit passes is 1 memset + 1 + P kernel launches.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -65,34 +66,36 @@ DigitConsts make_consts(const KeyInfo& ki, bool descending) {
   return dc;
 }
 
+// Test / tuning switches below are std::atomic (relaxed): every sort call only READS them, the setters of the C-ABI
+// (b2s_set_*) may run on another host thread.  The per-launch timing hook (g_timing) stays single-threaded by contract.
 // Tuning hook: variant 0 is the production tuning; a -DB2S_TUNING build carries more points.
-int g_variant = [] {
+std::atomic<int> g_variant{[] {
   const char* e = std::getenv("B2S_VARIANT");
   return e ? std::atoi(e) : 0;
-}();
+}()};
 int tuning_variant() { return g_variant; }
 // B2S_SINGLE_TILE=0 sends small sorts through the multi-kernel path too (A/B runs, tests of that path at small n).
-bool g_single_tile = [] {
+std::atomic<bool> g_single_tile{[] {
   const char* e = std::getenv("B2S_SINGLE_TILE");
   return !(e && e[0] == '0');
-}();
+}()};
 // Tile ids of the digit pass: block index (default; CTAs are dispatched in index order, the assumption CUB's decoupled
 // look-back scan makes too) or an atomic ticket taken by every CTA (B2S_TILE_CLAIM=1 / b2s_set_tile_claim(1)): with
 // tickets a tile's predecessors are always running or finished whatever the dispatch order, at ~1.5 % of throughput.
 // B2S_SPLIT_BULK=0 keeps the partition pass on item stores (A/B runs of the multi-GPU exchange)
-bool g_split_bulk = [] {
+std::atomic<bool> g_split_bulk{[] {
   const char* e = std::getenv("B2S_SPLIT_BULK");
   return !(e && e[0] == '0');
-}();
-bool g_claim = [] {
+}()};
+std::atomic<bool> g_claim{[] {
   const char* e = std::getenv("B2S_TILE_CLAIM");
   return e && e[0] == '1';
-}();
+}()};
 // B2S_SKIP_CONSTANT=0 disables the constant-digit short circuit (A/B runs): every pass then ranks and scatters
-bool g_skip_constant = [] {
+std::atomic<bool> g_skip_constant{[] {
   const char* e = std::getenv("B2S_SKIP_CONSTANT");
   return !(e && e[0] == '0');
-}();
+}()};
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;

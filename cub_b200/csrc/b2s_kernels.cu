@@ -101,10 +101,10 @@ constexpr Variant variant_cfg(int vi) {
     // more CTAs per SM with the same per-thread shape (overlap of the latency phases: TMA wait, digit scan, look-back)
     case 18: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_PAIR};
     case 19: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_PAIR};
-    case 20: return Variant{288, scale_ipt<V>(40), 2, 8, 0, 0, PF_PAIR};
+    case 20: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_PAIR};
     case 21: return Variant{256, scale_ipt<V>(28), 3, 8, 0, 0, PF_PAIR};
-    case 22: return Variant{288, scale_ipt<V>(42), 2, 8, 0, 0, PF_PAIR};
-    case 23: return Variant{320, scale_ipt<V>(34), 2, 8, 0, 0, PF_PAIR};
+    case 22: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR};
+    case 23: return Variant{256, scale_ipt<V>(42), 2, 8, 0, 0, PF_PAIR};
     case 24: return Variant{256, scale_ipt<V>(44), 2, 12, 0, 0, PF_PAIR};
     case 25: return Variant{288, scale_ipt<V>(26), 4, 12, 0, 0, 0};
     case 26: return Variant{256, scale_ipt<V>(28), 4, 12, 0, 0, 0};
