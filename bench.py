@@ -216,6 +216,8 @@ def run_ours(a):
     b2s = _lib.load()
     n = 1 << int(os.environ.get("B2S_BENCH_LOG2N", "28"))
     peak, peak_src = measured_peak()
+    # host side of the end-to-end path: run on (and allocate pinned memory from) the GPU's own NUMA node
+    numa = cb.device_radix_sort.bind_host_to_gpu_numa_node(local) if os.environ.get("B2S_NUMA_BIND", "1") != "0" else {"skipped": "B2S_NUMA_BIND=0"}
 
     def barrier():
         if dist is not None:
@@ -317,7 +319,7 @@ def run_ours(a):
                     "h2d_bytes_per_step": n * (KBYTES + VBYTES), "d2h_bytes_per_step": n * (KBYTES + VBYTES),
                     "how": "HostSorter(depth=2): pinned host -> device, DoubleBuffer sort, device -> pinned host, "
                            "upload / sort / download on three streams, steps pipelined over two buffer sets",
-                    "result_sane": e2e_ok},
+                    "result_sane": e2e_ok, "host_numa": numa},
             "gpu_launches": (launches_per_step - 1) * a.steps,
             "roofline": {"bound": "hbm", "kernel": "digit_pass_kernel (one 8-bit digit pass, b2s_pass.cuh)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
@@ -480,7 +482,7 @@ def run_ours(a):
             "e2e": {"value": total / float(e2e.item()) / 1e6, "unit": "GKeys/s", "ms_per_step": float(e2e.item()),
                     "h2d_bytes_per_step": total * 8, "d2h_bytes_per_step": total * 8,
                     "how": "per rank: pinned host -> device, global sort, device -> pinned host; upload / sort / download on "
-                           "three streams, steps pipelined over two buffer sets"},
+                           "three streams, steps pipelined over two buffer sets", "host_numa_rank0": numa},
             "gpu_launches": launches * a.steps * world,
             "roofline": {"bound": "hbm", "kernel": "digit_pass_kernel (one 8-bit digit pass)", "achieved": None,
                          "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,

@@ -8,6 +8,7 @@
 // constants so that one kernel instantiation serves unsigned, signed, ascending and
 // descending keys of a given width (floating keys use a second instantiation).
 #pragma once
+#include <type_traits>
 #include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -81,6 +82,55 @@ struct DigitOp {
     return ((uint32_t)(k >> bit) ^ xor_digit) & mask;  // == ((k ^ xor_mask) >> bit) & mask
   }
 };
+
+// Digit functor of the multi-pass sort for FLOATING keys.  Between the first and the last digit pass the keys live in
+// the intermediate buffers as their bit-ordered image t = k ^ (sign(k) ? ~0 : HIGH) ^ xor_mask (a bijection: -0.0 and +0.0
+// keep distinct images), so the sign-dependent transform is paid once per sort instead of three times per key per pass;
+// a digit is then the collapse of the zero image (DigitOp above, same rule) + shift + mask.  The first pass converts on
+// the way in (raw_in), the last one on the way out (raw_out); results are bit-identical to converting in every pass, which
+// is what the reference does (Traits<fp>::TwiddleIn / TwiddleOut, cub/util_type.cuh:1078-1100).
+template <int KBYTES>
+struct OrderedFloatOp {
+  using W = typename WideOf<KBYTES>::type;
+  static constexpr bool kConverts = true;
+  static constexpr int kMaxDigit = 255;
+  static constexpr int KBITS = KBYTES * 8;
+  static constexpr int WBITS = sizeof(W) * 8;
+  static constexpr W ONES = KBYTES == 8 ? ~W(0) : (W)((1ull << (KBITS % 64)) - 1);
+  static constexpr W HIGH = W(1) << (KBITS - 1);
+  static constexpr W ZERO_IMG = ONES ^ HIGH;  // the image that shares its digits with HIGH (DigitOp: zero_img, without register garbage)
+  W xor_mask;     // ONES if descending else 0
+  uint32_t bit, mask;
+  int raw_in, raw_out;  // keys arrive / leave in their raw encoding (first / last pass of a sort)
+
+  __device__ __forceinline__ void prepare() {}
+  // raw key (zero-extended in the register) -> image, bits above the key cleared
+  __host__ __device__ __forceinline__ W to_image(W k) const {
+    const W m = KBYTES == 8 ? (W)((long long)k >> 63) : (W)((int)((unsigned int)k << (WBITS - KBITS)) >> 31);
+    return (k ^ (m | HIGH) ^ xor_mask) & ONES;
+  }
+  __host__ __device__ __forceinline__ W to_raw(W t) const {
+    const W o = t ^ xor_mask;  // ascending image: top bit set <=> the key was not negative
+    const W m = KBYTES == 8 ? (W)((long long)o >> 63) : (W)((int)((unsigned int)o << (WBITS - KBITS)) >> 31);
+    return (o ^ (~m | HIGH)) & ONES;
+  }
+  // digit of an IMAGE
+  __device__ __forceinline__ uint32_t operator()(W t) const {
+    const W c = t == ZERO_IMG ? HIGH : t;
+    return (uint32_t)(c >> bit) & mask;
+  }
+};
+
+template <typename OpT, typename = void>
+struct OpConverts { static constexpr bool value = false; };
+template <typename OpT>
+struct OpConverts<OpT, std::enable_if_t<OpT::kConverts>> { static constexpr bool value = true; };
+
+template <typename OpT, typename W>
+__device__ __forceinline__ W image_to_raw(const OpT& op, W t) {
+  if constexpr (OpConverts<OpT>::value) return op.to_raw(t);
+  else return t;
+}
 
 // Destination functor of the multi-GPU partition pass: "digit" = number of splitters that order at or before
 // this key, i.e. the rank the key is sent to.  Splitters are (key, source rank) pairs; a key equal to splitter

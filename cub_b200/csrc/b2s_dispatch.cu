@@ -312,6 +312,8 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     a.trace = (g_trace_pass == p) ? g_trace : nullptr;
     a.claim = g_claim;
     a.skip_flag = g_skip_constant ? ctrs + 1 + passes + p : nullptr;
+    a.raw_in = p == 0;
+    a.raw_out = p == passes - 1;
     e = ks->onesweep(variant, a, stream);
     if (e != cudaSuccess) return (int)e;
     g_last_launches++;

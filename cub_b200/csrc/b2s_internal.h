@@ -45,6 +45,7 @@ struct PassArgs {
   unsigned long long* trace;  // tuning builds: per-tile phase timestamps (u64[tiles][16]) of one selected pass, else null
   bool claim;                 // tile ids from an atomic ticket instead of the block index (see b2s_set_tile_claim)
   const unsigned int* skip_flag;  // DEVICE flag written by the histogram kernel: non-zero = every key has the same digit in this pass
+  bool raw_in, raw_out;       // floating keys: this pass reads / writes the raw encoding (first / last pass); images in between
 };
 
 // Whole sort of one small tile in a single launch (b2s_single_tile.cuh).

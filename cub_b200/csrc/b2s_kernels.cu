@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <set>
+#include <type_traits>
 #include <utility>
 
 #include "b2s_histogram.cuh"
@@ -67,12 +68,12 @@ constexpr Variant variant_cfg(int vi) {
   // (their transform needs registers) and pairs take fewer items per thread than integer keys alone.
   const bool small_pairs = V > 0 && K + V <= 8;
   const bool pair44 = K == 4 && V == 4;
-  const Variant d = V == 0                  ? Variant{384, scale_ipt<V>(F ? 22 : (K <= 4 ? 26 : 24)), 3, 12, 0, 0, 0}
-                    : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(F ? 22 : 24), 3, 12, 0, 0, 0}
-                    : pair44                ? Variant{256, (F ? 42 : 46) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR}  // (key, value) as one 64-bit store
-                    : (small_pairs && !F)   ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0}
-                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(F ? 40 : 44) - (OFF64 ? 2 : 0), 2, 8, 0, 0, 0}  // wide pairs: few threads, many items each
-                                            : Variant{384, scale_ipt<V>(F ? 18 : 20), 3, 12, 0, 0, 0};
+  const Variant d = V == 0                  ? Variant{384, scale_ipt<V>(K <= 4 ? 26 : 24), 3, 12, 0, 0, 0}
+                    : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(24), 3, 12, 0, 0, 0}
+                    : pair44                ? Variant{256, 46 - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR}  // (key, value) as one 64-bit store
+                    : small_pairs          ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0}
+                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(44) - (OFF64 ? 2 : 0), 2, 8, 0, 0, 0}  // wide pairs: few threads, many items each
+                                            : Variant{384, scale_ipt<V>(20), 3, 12, 0, 0, 0};
 #ifdef B2S_TUNING
   constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);  // lab kernel: the round-1 production flow
   switch (vi) {
@@ -157,6 +158,25 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   return op;
 }
 
+// Functor of the multi-pass sort's digit passes: floating keys travel between passes as their bit-ordered image.
+template <bool F>
+using PassOp = std::conditional_t<F, OrderedFloatOp<K>, DigitOp<K, false>>;
+template <bool F>
+PassOp<F> make_pass_op(const PassArgs& a) {
+  if constexpr (F) {
+    using W = typename WideOf<K>::type;
+    OrderedFloatOp<K> op;
+    op.xor_mask = (W)a.dc.xor_mask;
+    op.bit = (uint32_t)a.bit;
+    op.mask = a.nbits >= 32 ? 0xffffffffu : (1u << a.nbits) - 1u;
+    op.raw_in = a.raw_in ? 1 : 0;
+    op.raw_out = a.raw_out ? 1 : 0;
+    return op;
+  } else {
+    return make_op<false>(a.dc, a.bit, a.nbits);
+  }
+}
+
 // Opt a kernel in to its dynamic shared-memory size once per (kernel, device); thread-safe.
 template <typename KernT>
 cudaError_t ensure_smem(KernT kern, int bytes) {
@@ -210,8 +230,8 @@ template <int V, bool F, typename OffT, int VI>
 cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   constexpr Variant c = variant_cfg<V, F, sizeof(OffT) == 8>(VI);
   constexpr int TILE = c.nt * c.ipt;
-  OnesweepParams<K, DigitOp<K, F>> p;
-  fill_params(p, a, make_op<F>(a.dc, a.bit, a.nbits));
+  OnesweepParams<K, PassOp<F>> p;
+  fill_params(p, a, make_pass_op<F>(a));
   const unsigned long long tiles = (a.n + TILE - 1) / TILE;
   // 64-bit look-back words cost two registers each: half the window
   constexpr int LBW = (sizeof(OffT) == 8 && c.lbw > 4) ? c.lbw / 2 : c.lbw;
@@ -238,11 +258,11 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
       return cudaGetLastError();
     };
 #ifdef B2S_TUNING
-    return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL, (c.abl > 0 ? c.abl : 222)>);  // abl = L2 prefetch distance
+    return launch(digit_pass_kernel<K, V, PassOp<F>, OffT, c.nt, c.ipt, c.minb, LBW, FL, (c.abl > 0 ? c.abl : 222)>);  // abl = L2 prefetch distance
 #else
     // ticketed tile ids on request (b2s_set_tile_claim / B2S_TILE_CLAIM=1): no reliance on in-order CTA dispatch
-    if (a.claim) return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL | PF_CLAIM>);
-    return launch(digit_pass_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, FL>);
+    if (a.claim) return launch(digit_pass_kernel<K, V, PassOp<F>, OffT, c.nt, c.ipt, c.minb, LBW, FL | PF_CLAIM>);
+    return launch(digit_pass_kernel<K, V, PassOp<F>, OffT, c.nt, c.ipt, c.minb, LBW, FL>);
 #endif
   }
 }

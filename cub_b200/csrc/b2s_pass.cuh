@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   constexpr bool TMAW = (FLAGS & PF_TMAW) != 0 && !PAIR && KBYTES >= 4 && (VBYTES == 0 || VBYTES == 4 || VBYTES == 8);
   constexpr bool CLAIM = (FLAGS & PF_CLAIM) != 0;
   constexpr bool PEER = (FLAGS & PF_PEER) != 0;
+  constexpr bool CONV = OpConverts<OpT>::value;  // floating keys travel as bit-ordered images between passes (OrderedFloatOp)
+  static_assert(!(CONV && (TMAW || PEER)), "image-form keys: plain digit passes only");
   using KeyU = typename UIntOf<KBYTES>::type;
   using W = typename WideOf<KBYTES>::type;
   using ValU = typename UIntOf<VBYTES ? VBYTES : 1>::type;
@@ -275,7 +277,11 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
     KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
     // a partial tile is padded with a key whose digit is the largest one in every pass: the padding ranks after all
     // real items and is never written out
-    for (int i = tid; i < TILE; i += NT) sk[i] = i < valid ? gkeys[i] : (KeyU)P.pad_key;
+    KeyU pad = (KeyU)P.pad_key;
+    if constexpr (CONV) {
+      if (!P.op.raw_in) pad = (KeyU)OpT::ONES;  // keys arrive as images: all ones orders last
+    }
+    for (int i = tid; i < TILE; i += NT) sk[i] = i < valid ? gkeys[i] : pad;
     if (HAS_VALUES) {
       ValU* sv = reinterpret_cast<ValU*>(stage_v);
       for (int i = tid; i < valid; i += NT) sv[i] = gvals[i];
@@ -298,8 +304,17 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
     }
     const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + (g.bulk ? g.kshift : 0u));
     KeyU* ok = reinterpret_cast<KeyU*>(P.keys_out) + g.base;
+    int conv = 0;  // a copy still converts when the encodings of its input and output differ
+    if constexpr (CONV) conv = P.op.raw_in == P.op.raw_out ? 0 : (P.op.raw_in ? 1 : 2);
+    if (conv == 0) {
 #pragma unroll 4
-    for (int i = tid; i < valid; i += NT) ok[i] = sk[i];
+      for (int i = tid; i < valid; i += NT) ok[i] = sk[i];
+    } else {
+      if constexpr (CONV) {
+#pragma unroll 4
+        for (int i = tid; i < valid; i += NT) ok[i] = (KeyU)(conv == 1 ? P.op.to_image((W)sk[i]) : P.op.to_raw((W)sk[i]));
+      }
+    }
     if (HAS_VALUES) {
       const ValU* sv = reinterpret_cast<const ValU*>(stage_v + (g.bulk ? g.vshift : 0u));
       ValU* ov = reinterpret_cast<ValU*>(P.vals_out) + g.base;
@@ -321,6 +336,12 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   }
   auto op = P.op;
   op.prepare();  // no-op for DigitOp; loads the device-resident splitters for SplitterOp
+  if constexpr (CONV) {
+    if (op.raw_in) {
+#pragma unroll
+      for (int u = 0; u < IPT; ++u) key[u] = op.to_image(key[u]);
+    }
+  }
   unsigned int* myhist = whist + warp * RADIX;
   const unsigned int myhist_s = smem_u32(myhist);
   const unsigned int lt = lanemask_lt();
@@ -480,7 +501,7 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   } else {
     const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k);
     const ValU* sv = reinterpret_cast<const ValU*>(stage_v);
-    auto emit = [&](int pos) {
+    auto emit = [&](int pos, auto to_raw) {
       KeyU k;
       ValU v{};
       if constexpr (PAIR) {
@@ -498,17 +519,26 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
         okeys = reinterpret_cast<KeyU*>(P.peer_keys[d & (MAX_PEERS - 1)]);
         ovals = reinterpret_cast<ValU*>(P.peer_vals[d & (MAX_PEERS - 1)]);
       }
+      if constexpr (CONV && decltype(to_raw)::value) k = (KeyU)image_to_raw(op, (W)k);
       okeys[dst] = k;
       if constexpr (HAS_VALUES) ovals[dst] = v;
     };
-    const TileGeom g = geom(tile_now());
-    const int valid = g.full ? TILE : (int)g.remain;
-    if (g.full) {
+    auto emit_all = [&](auto to_raw) {
+      const TileGeom g = geom(tile_now());
+      const int valid = g.full ? TILE : (int)g.remain;
+      if (g.full) {
 #pragma unroll
-      for (int u = 0; u < IPT; ++u) emit(u * NT + tid);
-    } else {
+        for (int u = 0; u < IPT; ++u) emit(u * NT + tid, to_raw);
+      } else {
 #pragma unroll 1
-      for (int pos = tid; pos < valid; pos += NT) emit(pos);
+        for (int pos = tid; pos < valid; pos += NT) emit(pos, to_raw);
+      }
+    };
+    if constexpr (CONV) {
+      if (op.raw_out) emit_all(std::true_type{});
+      else emit_all(std::false_type{});
+    } else {
+      emit_all(std::false_type{});
     }
   }
 }

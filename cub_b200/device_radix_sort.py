@@ -318,6 +318,32 @@ def sort_keys(keys: torch.Tensor, descending: bool = False, begin_bit: int = 0, 
     return sort_pairs(keys, None, descending, begin_bit, end_bit, stream)[0]
 
 
+def bind_host_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPU cores of the NUMA node the GPU hangs off, BEFORE pinned host buffers are
+    allocated (first touch then places them in that node's memory): host<->device copies of the end-to-end path then do
+    not cross the socket interconnect.  Host-side deployment plumbing, no effect on results.  Returns what was done
+    ({"numa_node": n, "cpus": k} or {"skipped": reason}); never raises."""
+    import os
+
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"skipped": "no NUMA affinity reported for " + bdf}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"skipped": f"no allowed CPU on NUMA node {node}"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed), "pci": bdf}
+    except Exception as e:  # noqa: BLE001
+        return {"skipped": str(e)[:100]}
+
+
 class HostSorter:
     """End-to-end path with HOST buffers: pinned host -> device, DoubleBuffer sort, device -> pinned host.
     Device buffers, temp storage and pinned result buffers are allocated once and reused (what a caller of the
