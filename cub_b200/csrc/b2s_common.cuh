@@ -400,4 +400,10 @@ __device__ __forceinline__ uint32_t atoms_add_if(bool pred, uint32_t smem_addr, 
   return old;
 }
 
+__device__ __forceinline__ uint32_t atoms_add(uint32_t smem_addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr), "r"(v) : "memory");
+  return old;
+}
+
 }  // namespace b2s

@@ -64,15 +64,21 @@ template <int V, bool F = false, bool OFF64 = false>
 constexpr Variant variant_cfg(int vi) {
   // {threads, items/thread, min CTAs/SM, look-back window, -, lab mode, flow}.  flow >= 0: production kernel with these
   // PF_* flags; flow < 0: laboratory kernel with `mode` (tuning builds).  Shapes from the B200 sweeps in
-  // profiles/r1_tune_sweep_*.jsonl and profiles/r2_*.jsonl.  A variant that spills loses 15-25 %, so floating keys
-  // (their transform needs registers) and pairs take fewer items per thread than integer keys alone.
+  // profiles/r1_tune_sweep_*.jsonl and profiles/r2_*.jsonl.  A variant that spills loses 15-25 %.  Pairs want few threads
+  // with many items each (2 CTAs x 256 threads: no warp idles while 256 threads scan and look back, larger tiles);
+  // keys alone want more warps (3 CTAs x 320).  Floating keys use the integer shapes (OrderedFloatOp).
   const bool small_pairs = V > 0 && K + V <= 8;
   const bool pair44 = K == 4 && V == 4;
-  const Variant d = V == 0                  ? Variant{384, scale_ipt<V>(K <= 4 ? 26 : 24), 3, 12, 0, 0, 0}
-                    : (K + V <= 6 && V >= 2) ? Variant{384, scale_ipt<V>(24), 3, 12, 0, 0, 0}
-                    : pair44                ? Variant{256, 46 - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR}  // (key, value) as one 64-bit store
+  // (round-2 sweeps: profiles/r2_tune_shapes_*.jsonl, r2_tune_nobr.jsonl)
+  // keys alone: integer keys of >= 2 bytes 320 x 30 x 3 with the branch-free ranking atomic (+2.5-6 %); 1-byte keys and
+  // floating keys (one more compare per digit) measured faster at 384 x 26 x 3 with the predicated atomic
+  const Variant d = V == 0                  ? ((K == 1 || F) ? Variant{384, scale_ipt<V>(K <= 4 ? 26 : 24), 3, 12, 0, 0, 0}
+                                                             : Variant{320, scale_ipt<V>(30) - (OFF64 ? 2 : 0), 3, 12, 0, 0, PF_NOBR})
+                    : (K + V <= 6 && V >= 2) ? (F ? Variant{384, scale_ipt<V>(24), 3, 12, 0, 0, 0}
+                                                  : Variant{320, scale_ipt<V>(30) - (OFF64 ? 4 : 0), 3, 12, 0, 0, PF_NOBR})
+                    : pair44                ? Variant{256, (F ? 40 : 48) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR | PF_NOBR}  // (key, value) as one 64-bit store
                     : small_pairs          ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0}
-                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(44) - (OFF64 ? 2 : 0), 2, 8, 0, 0, 0}  // wide pairs: few threads, many items each
+                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(44) - (OFF64 ? 2 : 0), 2, 8, 0, 0, PF_NOBR}  // wide pairs: few threads, many items each
                                             : Variant{384, scale_ipt<V>(20), 3, 12, 0, 0, 0};
 #ifdef B2S_TUNING
   constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);  // lab kernel: the round-1 production flow
@@ -100,15 +106,15 @@ constexpr Variant variant_cfg(int vi) {
     case 16: return Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0};
     case 17: return Variant{256, scale_ipt<V>(26), 4, 12, 0, 0, 0};
     // more CTAs per SM with the same per-thread shape (overlap of the latency phases: TMA wait, digit scan, look-back)
-    case 18: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_PAIR};
-    case 19: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_PAIR};
-    case 20: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_PAIR};
+    case 18: return Variant{d.nt, d.ipt, d.minb, d.lbw, 0, 0, d.flow | PF_NOBR};
+    case 19: return Variant{320, scale_ipt<V>(30), 3, 12, 0, 0, PF_NOBR};
+    case 20: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
     case 21: return Variant{256, scale_ipt<V>(28), 3, 8, 0, 0, PF_PAIR};
-    case 22: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR};
-    case 23: return Variant{256, scale_ipt<V>(42), 2, 8, 0, 0, PF_PAIR};
-    case 24: return Variant{256, scale_ipt<V>(44), 2, 12, 0, 0, PF_PAIR};
-    case 25: return Variant{288, scale_ipt<V>(26), 4, 12, 0, 0, 0};
-    case 26: return Variant{256, scale_ipt<V>(28), 4, 12, 0, 0, 0};
+    case 22: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
+    case 23: return Variant{256, scale_ipt<V>(46), 2, 12, 0, 0, PF_PAIR | PF_NOBR};
+    case 24: return Variant{256, scale_ipt<V>(46), 2, 4, 0, 0, PF_PAIR | PF_NOBR};
+    case 25: return Variant{384, scale_ipt<V>(28), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
+    case 26: return Variant{256, scale_ipt<V>(28), 3, 8, 0, 0, PF_PAIR | PF_NOBR};
     case 27: return Variant{320, scale_ipt<V>(30), 3, 12, 0, 0, 0};
     case 28: return Variant{384, scale_ipt<V>(28), 3, 12, 0, 0, 0};
     case 29: return Variant{512, scale_ipt<V>(28), 2, 12, 0, 0, 0};

@@ -42,6 +42,7 @@ enum : int {
   PF_TMAW = 2,   // write-out by bulk shared->global copies (keys / values of 4 or 8 bytes)
   PF_CLAIM = 4,  // tile id = atomic ticket instead of the block index (no reliance on in-order CTA dispatch)
   PF_PEER = 8,   // per-destination output bases (multi-GPU partition pass)
+  PF_NOBR = 16,  // ranking atomic issued by every lane (non-leaders add to a private scratch word): no branch around it
 };
 
 template <int KBYTES, typename OpT>
@@ -82,7 +83,8 @@ struct PassSmem {
   static constexpr int OFF_GOFF = OFF_WHIST + NW * RADIX * 4;   // OffT[256] (8 bytes reserved each)
   static constexpr int OFF_RUN = OFF_GOFF + RADIX * 8;          // TMAW: uint32[256] = slot start | length << 16
   static constexpr int OFF_MISC = OFF_RUN + (TMAW ? RADIX * 4 : 0);
-  static constexpr int TOTAL = OFF_MISC + 128;                  // barriers, scan partials, tile id
+  static constexpr int OFF_DUMMY = OFF_MISC + 128;              // PF_NOBR: one scratch word per lane and warp
+  static constexpr int TOTAL = OFF_DUMMY + NW * 128;            // barriers, scan partials, tile id
   static_assert(SLOTS < 65536, "tile positions are 16-bit");
 };
 
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   constexpr bool TMAW = (FLAGS & PF_TMAW) != 0 && !PAIR && KBYTES >= 4 && (VBYTES == 0 || VBYTES == 4 || VBYTES == 8);
   constexpr bool CLAIM = (FLAGS & PF_CLAIM) != 0;
   constexpr bool PEER = (FLAGS & PF_PEER) != 0;
+  constexpr bool NOBR = (FLAGS & PF_NOBR) != 0;
   constexpr bool CONV = OpConverts<OpT>::value;  // floating keys travel as bit-ordered images between passes (OrderedFloatOp)
   static_assert(!(CONV && (TMAW || PEER)), "image-form keys: plain digit passes only");
   using KeyU = typename UIntOf<KBYTES>::type;
@@ -440,7 +443,13 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
     for (int u = 0; u < IPT; ++u) {
       const unsigned int leader = bfind(m);
       const unsigned int below = __popc(m & lt);
-      const unsigned int raw = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
+      unsigned int raw;
+      if constexpr (NOBR) {
+        const unsigned int scratch = smem_u32(smem + L::OFF_DUMMY) + (unsigned int)tid * 4u;
+        raw = atoms_add(lane == leader ? myhist_s + d * 4 : scratch, (unsigned int)__popc(m));
+      } else {
+        raw = atoms_add_if(lane == leader, myhist_s + d * 4, (unsigned int)__popc(m));
+      }
       unsigned int d_next = 0, m_next = 0;
       if (u + 1 < IPT) {
         d_next = op(key[u + 1]);
