@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_MISC);                  // [2]
   unsigned int* s_wtot = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 16);  // [8]
   unsigned int* s_tile = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 64);
+  unsigned int* s_geom = reinterpret_cast<unsigned int*>(smem + L::OFF_MISC + 68);  // tile summary, written once by thread 0
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -243,6 +244,8 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
     mbar_init(&bar[1], 1);
     mbar_fence_init();
     const TileGeom g = geom(t0);
+    // what the later phases need to know about the tile, so that nobody re-derives the 64-bit geometry
+    *s_geom = (g.bulk ? 1u : 0u) | (g.full ? 2u : 0u) | (g.bulk ? (g.kshift << 8) | (g.vshift << 16) : 0u);
     if (g.bulk) {
       mbar_expect_tx(&bar[0], g.kbytes);
       bulk_g2s(stage_k, reinterpret_cast<const void*>(g.kaddr - g.kshift), g.kbytes, &bar[0]);
@@ -256,25 +259,31 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   for (int i = tid; i < NW * RADIX; i += NT) whist[i] = 0;
   __syncthreads();
 
-  // The tile id and everything derived from it is RE-derived in every phase instead of being carried in registers: free
-  // with block-index ids (special register), one shared-memory load with tickets -- the ranking sweep needs the registers.
+  // The tile id is re-read in every phase instead of being carried in a register (special register with block-index ids,
+  // one shared-memory load with tickets) -- the ranking sweep needs the registers.
   auto tile_now = [&]() -> unsigned long long {
     if (CLAIM) return (unsigned long long)*reinterpret_cast<volatile unsigned int*>(s_tile);
     return (unsigned long long)blockIdx.x;
   };
-  {
-  const unsigned long long tile = tile_now();
-  const TileGeom g = geom(tile);
-  const int valid = g.full ? TILE : (int)g.remain;
-  if (PFD && tid == 32 && tile + PFD + 1 < num_tiles) {
+  // tile summary (bit 0 bulk copies in flight, bit 1 full tile, bits 8-11 / 16-19 byte shift of the staged keys / values):
+  // one shared-memory load where it is needed instead of the 64-bit geometry or four live registers
+  auto tile_summary = [&]() -> unsigned int { return *reinterpret_cast<volatile unsigned int*>(s_geom); };
+  const bool t_bulk = (tile_summary() & 1u) != 0;
+  if (PFD && tid == 32) {
+    const unsigned long long tile = tile_now();
+    const TileGeom g = geom(tile);
+    if (tile + PFD + 1 < num_tiles) {
     // ask L2 for a tile that will start about one CTA lifetime from now, so that its TMA copies hit L2
     bulk_prefetch_l2(reinterpret_cast<const void*>((g.kaddr + (unsigned long long)PFD * TILE * KBYTES) & ~(uintptr_t)15),
                      (unsigned int)(TILE * KBYTES) & ~15u);
     if (HAS_VALUES)
       bulk_prefetch_l2(reinterpret_cast<const void*>((g.vaddr + (unsigned long long)PFD * TILE * VBYTES) & ~(uintptr_t)15),
                        (unsigned int)(TILE * VBYTES) & ~15u);
+    }
   }
-  if (!g.bulk) {
+  if (!t_bulk) {
+    const TileGeom g = geom(tile_now());
+    const int valid = g.full ? TILE : (int)g.remain;
     const KeyU* gkeys = reinterpret_cast<const KeyU*>(g.kaddr);
     const ValU* gvals = reinterpret_cast<const ValU*>(g.vaddr);
     KeyU* sk = reinterpret_cast<KeyU*>(stage_k);
@@ -290,7 +299,6 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
       for (int i = tid; i < valid; i += NT) sv[i] = gvals[i];
     }
     __syncthreads();
-  }
   }
 
   // ---- constant-digit pass (flag from the upfront histogram): the stable partition is the identity -- copy the staged
@@ -331,9 +339,9 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   const int warp_base = warp * 32 * IPT;
   W key[IPT];
   {
-    const TileGeom g = geom(tile_now());
-    if (g.bulk) mbar_wait(&bar[0], 0);
-    const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + (g.bulk ? g.kshift : 0u));
+    const unsigned int gs = tile_summary();
+    if (gs & 1u) mbar_wait(&bar[0], 0);
+    const KeyU* sk = reinterpret_cast<const KeyU*>(stage_k + ((gs >> 8) & 15u));  // the shift is zero without bulk copies
 #pragma unroll
     for (int u = 0; u < IPT; ++u) key[u] = (W)sk[warp_base + u * 32 + lane];
   }
@@ -353,9 +361,9 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
 
   ValU val[HAS_VALUES ? IPT : 1];
   auto load_values = [&]() {
-    const TileGeom g = geom(tile_now());
-    if (g.bulk) mbar_wait(&bar[1], 0);
-    const ValU* sv = reinterpret_cast<const ValU*>(stage_v + (g.bulk ? g.vshift : 0u));
+    const unsigned int gs = tile_summary();
+    if (gs & 1u) mbar_wait(&bar[1], 0);
+    const ValU* sv = reinterpret_cast<const ValU*>(stage_v + ((gs >> 16) & 15u));
 #pragma unroll
     for (int u = 0; u < IPT; ++u) val[u] = sv[warp_base + u * 32 + lane];
   };
@@ -533,12 +541,11 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
       if constexpr (HAS_VALUES) ovals[dst] = v;
     };
     auto emit_all = [&](auto to_raw) {
-      const TileGeom g = geom(tile_now());
-      const int valid = g.full ? TILE : (int)g.remain;
-      if (g.full) {
+      if (tile_summary() & 2u) {
 #pragma unroll
         for (int u = 0; u < IPT; ++u) emit(u * NT + tid, to_raw);
       } else {
+        const int valid = (int)geom(tile_now()).remain;
 #pragma unroll 1
         for (int pos = tid; pos < valid; pos += NT) emit(pos, to_raw);
       }
