@@ -111,8 +111,8 @@ constexpr Variant variant_cfg(int vi) {
     case 20: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
     case 21: return Variant{256, scale_ipt<V>(28), 3, 8, 0, 0, PF_PAIR};
     case 22: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
-    case 23: return Variant{256, scale_ipt<V>(46), 2, 12, 0, 0, PF_PAIR | PF_NOBR};
-    case 24: return Variant{256, scale_ipt<V>(46), 2, 4, 0, 0, PF_PAIR | PF_NOBR};
+    case 23: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
+    case 24: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
     case 25: return Variant{384, scale_ipt<V>(28), 2, 8, 0, 0, PF_PAIR | PF_NOBR};
     case 26: return Variant{256, scale_ipt<V>(28), 3, 8, 0, 0, PF_PAIR | PF_NOBR};
     case 27: return Variant{320, scale_ipt<V>(30), 3, 12, 0, 0, 0};
