@@ -102,7 +102,7 @@ def sass(obj, pattern, out):
     return syms[0]
 
 B = os.path.join(ROOT, "cub_b200", "csrc", "build")
-print(sass(os.path.join(B, "k4.o"), r"digit_pass_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEjLi448ELi24ELi2ELi8ELi1E", os.path.join(P, f"{PFX}_digit_pass_u32_u32.sass")))
+print(sass(os.path.join(B, "k4.o"), r"digit_pass_kernelILi4ELi4ENS_7DigitOpILi4ELb0EEEjLi256ELi48ELi2ELi8ELi17E", os.path.join(P, f"{PFX}_digit_pass_u32_u32.sass")))
 print(sass(os.path.join(B, "k4.o"), r"histogram_kernelILi4ELb0EjLb1", os.path.join(P, f"{PFX}_histogram_u32.sass")))
 print(open(os.path.join(P, f"{PFX}_launches_bench.txt")).read())
 
