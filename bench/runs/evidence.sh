@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, run l: evidence for profiles/ with the summaries extracted ON the box (three --import-source reports exceed the
+# evidence for profiles/ with the summaries extracted ON the box (three --import-source reports exceed the
 # 64 MiB that gpurun copies back): launch list of the bench command, ncu --set full of the production kernels, bench lines
 TAG=${1:-r2l}
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, run q: GPU tests + bench + configs table with the 256-thread pair shapes
+# GPU tests + bench + configs table with the 256-thread pair shapes
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${1:-r2q}.json 2> gpurun_out/bench_${1:-r2q}.err; echo "bench exit $?"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, run r: ncu --set full of the 256 x 46 x 2 pair kernel (summaries extracted on the box)
+# ncu --set full of the 256 x 46 x 2 pair kernel (summaries extracted on the box)
 TAG=${1:-r2r}
 mkdir -p gpurun_out
 N32=$((1 << 23))
