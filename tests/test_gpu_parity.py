@@ -318,6 +318,36 @@ def test_config3_pairs_u64_2p30_partial_bits(b2s):
     assert bool((v_out[1:][same] > v_out[:-1][same]).all())
 
 
+@pytest.mark.parametrize("kt", [6, 8], ids=["u32", "f32"])
+def test_pair_flow_with_64bit_offsets_2p30(b2s, refcub, kt):
+    """4-byte keys with 4-byte values at n = 2^30: the pair flow (one 64-bit shared-memory store per item) with 64-bit
+    look-back words and offsets (its own instantiation: fewer items per thread, half the window); for f32 keys also the
+    image-form intermediate buffers.  DoubleBuffer form, bit-exact against the reference on the same input."""
+    n = 1 << 30
+    free, _ = torch.cuda.mem_get_info()
+    if free < 48 * (1 << 30):
+        pytest.skip("not enough device memory")
+    keys = H.gen_device_keys(b2s, n, 4, seed=4242)
+    if kt == 8:
+        idx = torch.arange(n, device="cuda")
+        keys[idx % 1024 == 0] = 0
+        keys[idx % 1024 == 1] = torch.iinfo(torch.int32).min  # -0.0
+        del idx
+    vals = H.gen_device_iota(b2s, n, 4)
+    inv0 = H.check_sorted(b2s, keys, vals, kt, True)
+    kb = [keys.clone(), torch.empty_like(keys)]
+    vb = [vals.clone(), torch.empty_like(vals)]
+    ks, vs = H.sort_db(b2s.b2s_radix_sort_db, kb, vb, kt, True)
+    inv = H.check_sorted(b2s, kb[ks], vb[vs], kt, True)
+    assert inv[0] == 0 and inv[1] == inv0[1] and inv[2] == inv0[2]
+    k_us, v_us = kb[ks], vb[vs]
+    del kb, vb
+    k_ref, v_ref = H.sort_ptr(refcub.sort, keys, vals, kt, True)
+    assert torch.equal(k_us, k_ref) and torch.equal(v_us, v_ref)
+    del k_us, v_us, k_ref, v_ref
+    torch.cuda.empty_cache()
+
+
 def test_config4_descending_float_2p29(b2s, refcub):
     n = 1 << 29
     for kt, nb in ((8, 4), (5, 2)):
