@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(SEG_NT, 2) segmented_sort_kernel(const Segment
     op.mask = (1u << nbits) - 1u;
     op.xor_digit = (uint32_t)(op.xor_mask >> bit) & op.mask;
   };
-  auto load_tile = [&](const KeyU* gk, const ValU* gv, int valid) {
+  auto load_tile = [&](const KeyU* gk, const ValU* gv, int valid, int slots) {
 #pragma unroll 4
-    for (int i = tid; i < TILE; i += NT) sk[i] = i < valid ? gk[i] : (KeyU)P.pad_key;
+    for (int i = tid; i < slots; i += NT) sk[i] = i < valid ? gk[i] : (KeyU)P.pad_key;
     if (HAS_VALUES) {
 #pragma unroll 4
       for (int i = tid; i < valid; i += NT) sv[i] = gv[i];
@@ -194,11 +194,16 @@ __global__ void __launch_bounds__(SEG_NT, 2) segmented_sort_kernel(const Segment
 
   if (len <= (unsigned long long)TILE) {
     // ---- the whole segment is one tile: every pass in shared memory
+    // The tile pass is instantiated for 1, 4 and 16 items per thread: a segment of <= 256 / <= 1024 items is padded to and
+    // worked on as a 256- / 1024-slot tile instead of the full 4096 (a 64-item segment: 8 rows of 32 instead of 128).
     const int n = (int)len;
-    load_tile(reinterpret_cast<const KeyU*>(P.keys_src) + begin, reinterpret_cast<const ValU*>(P.vals_src) + begin, n);
+    const int slots = n <= NT ? NT : (n <= NT * 4 ? NT * 4 : TILE);
+    load_tile(reinterpret_cast<const KeyU*>(P.keys_src) + begin, reinterpret_cast<const ValU*>(P.vals_src) + begin, n, slots);
     for (int p = 0; p < P.passes; ++p) {
       set_pass(p);
-      tile_digit_pass<KBYTES, VBYTES, NT, SEG_IPT>(sk, sv, whist, s_wtot, op, P.ones, nullptr);
+      if (slots == NT) tile_digit_pass<KBYTES, VBYTES, NT, 1>(sk, sv, whist, s_wtot, op, P.ones, nullptr);
+      else if (slots == NT * 4) tile_digit_pass<KBYTES, VBYTES, NT, 4>(sk, sv, whist, s_wtot, op, P.ones, nullptr);
+      else tile_digit_pass<KBYTES, VBYTES, NT, SEG_IPT>(sk, sv, whist, s_wtot, op, P.ones, nullptr);
     }
     KeyU* gk = reinterpret_cast<KeyU*>(P.keys_a) + begin;
     for (int i = tid; i < n; i += NT) gk[i] = sk[i];
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(SEG_NT, 2) segmented_sort_kernel(const Segment
     __syncthreads();
     for (unsigned long long t0 = 0; t0 < len; t0 += TILE) {
       const int valid = (len - t0) < (unsigned long long)TILE ? (int)(len - t0) : TILE;
-      load_tile(src_k + t0, src_v + t0, valid);
+      load_tile(src_k + t0, src_v + t0, valid, TILE);
       tile_digit_pass<KBYTES, VBYTES, NT, SEG_IPT>(sk, sv, whist, s_wtot, op, P.ones, s_dstart);
       for (int pos = tid; pos < valid; pos += NT) {
         const KeyU k = sk[pos];
