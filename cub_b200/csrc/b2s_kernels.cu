@@ -70,10 +70,11 @@ constexpr Variant variant_cfg(int vi) {
   const bool small_pairs = V > 0 && K + V <= 8;
   const bool pair44 = K == 4 && V == 4;
   // (round-2 sweeps: profiles/r2_tune_shapes_*.jsonl, r2_tune_nobr.jsonl)
-  // keys alone: integer keys of >= 2 bytes 320 x 30 x 3 with the branch-free ranking atomic (+2.5-6 %); 1-byte keys and
-  // floating keys (one more compare per digit) measured faster at 384 x 26 x 3 with the predicated atomic
-  const Variant d = V == 0                  ? ((K == 1 || F) ? Variant{384, scale_ipt<V>(K <= 4 ? 26 : 24), 3, 12, 0, 0, 0}
-                                                             : Variant{320, scale_ipt<V>(30) - (OFF64 ? 2 : 0), 3, 12, 0, 0, PF_NOBR})
+  // keys alone: 256 threads x 60 items x 3 CTAs/SM with the branch-free ranking atomic (8-byte keys: 256 x 48 x 2): every
+  // warp scans and looks back, 15360-key tiles; +11-12 % over 320 x 30 x 3 / 384 x 26 x 3 (profiles/r2_tune_shapes_keys_256thr.jsonl)
+  const Variant d = V == 0                  ? (F ? Variant{384, scale_ipt<V>(K <= 4 ? 26 : 24), 3, 12, 0, 0, 0}  // floating keys: measured best (spills at 256 x 44+)
+                                                 : K == 8 ? Variant{256, 48 - (OFF64 ? 4 : 0), 2, 12, 0, 0, PF_NOBR}
+                                                          : Variant{256, 60 - (OFF64 ? 4 : 0), 3, 8, 0, 0, PF_NOBR})
                     : (K + V <= 6 && V >= 2) ? (F ? Variant{384, scale_ipt<V>(24), 3, 12, 0, 0, 0}
                                                   : Variant{320, scale_ipt<V>(30) - (OFF64 ? 4 : 0), 3, 12, 0, 0, PF_NOBR})
                     : pair44                ? Variant{256, (F ? 40 : 48) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR | PF_NOBR}  // (key, value) as one 64-bit store
@@ -132,18 +133,18 @@ constexpr Variant variant_cfg(int vi) {
     case 38: return Variant{512, scale_ipt<V>(20), 2, 4, 4, 0, -1};
     case 39: return Variant{512, scale_ipt<V>(20), 2, 4, 8, 0, -1};
     // round 2, second shape sweep around 256 x 28 x 3 (pairs) -- fewer threads, more items per thread
-    case 40: return Variant{256, scale_ipt<V>(28), 3, 12, 0, 0, PF_PAIR};
-    case 41: return Variant{256, scale_ipt<V>(28), 3, 6, 0, 0, PF_PAIR};
-    case 42: return Variant{256, scale_ipt<V>(26), 3, 8, 0, 0, PF_PAIR};
-    case 43: return Variant{256, scale_ipt<V>(44), 2, 6, 0, 0, PF_PAIR};
-    case 44: return Variant{256, scale_ipt<V>(44), 2, 8, 0, 0, PF_PAIR};
-    case 45: return Variant{384, scale_ipt<V>(28), 2, 8, 0, 0, PF_PAIR};
-    case 46: return Variant{256, scale_ipt<V>(42), 2, 8, 0, 0, PF_PAIR};
+    case 40: return Variant{256, scale_ipt<V>(26), 3, 8, 0, 0, PF_NOBR};
+    case 41: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_NOBR};
+    case 42: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_NOBR};
+    case 43: return Variant{256, scale_ipt<V>(40), 2, 8, 0, 0, PF_NOBR};
+    case 44: return Variant{256, scale_ipt<V>(24), 3, 8, 0, 0, PF_NOBR};
+    case 45: return Variant{256, scale_ipt<V>(72), 2, 12, 0, 0, PF_NOBR};
+    case 46: return Variant{256, scale_ipt<V>(36), 3, 12, 0, 0, PF_NOBR};
     case 47: return Variant{256, scale_ipt<V>(44), 2, 8, 148, 0, PF_PAIR};
     case 50: return Variant{256, scale_ipt<V>(44), 2, 8, 296, 0, PF_PAIR};
-    case 51: return Variant{256, scale_ipt<V>(36), 3, 12, 0, 0, 0};
-    case 48: return Variant{256, scale_ipt<V>(32), 3, 12, 0, 0, 0};
-    case 49: return Variant{256, scale_ipt<V>(40), 2, 12, 0, 0, 0};
+    case 51: return Variant{256, scale_ipt<V>(56), 3, 12, 0, 0, PF_NOBR};
+    case 48: return Variant{256, scale_ipt<V>(48), 3, 12, 0, 0, PF_NOBR};
+    case 49: return Variant{256, scale_ipt<V>(60), 2, 12, 0, 0, PF_NOBR};
     default: return d;
   }
 #else
