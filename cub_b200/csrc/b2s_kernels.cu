@@ -79,7 +79,7 @@ constexpr Variant variant_cfg(int vi) {
                                                   : Variant{320, scale_ipt<V>(30) - (OFF64 ? 4 : 0), 3, 12, 0, 0, PF_NOBR})
                     : pair44                ? Variant{256, (F ? 40 : 48) - (OFF64 ? 4 : 0), 2, 8, 0, 0, PF_PAIR | PF_NOBR}  // (key, value) as one 64-bit store
                     : small_pairs          ? Variant{512, scale_ipt<V>(22), 2, 12, 0, 0, 0}
-                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(44) - (OFF64 ? 2 : 0), 2, 8, 0, 0, PF_NOBR}  // wide pairs: few threads, many items each
+                    : (K + V >= 12)         ? Variant{256, scale_ipt<V>(48) - (OFF64 ? 2 : 0), 2, 8, 0, 0, PF_NOBR}  // wide pairs: few threads, many items each
                                             : Variant{384, scale_ipt<V>(20), 3, 12, 0, 0, 0};
 #ifdef B2S_TUNING
   constexpr int M = 8 | 32 | 64 | 128 | 256 | (222 << 16);  // lab kernel: the round-1 production flow
@@ -133,12 +133,12 @@ constexpr Variant variant_cfg(int vi) {
     case 38: return Variant{512, scale_ipt<V>(20), 2, 4, 4, 0, -1};
     case 39: return Variant{512, scale_ipt<V>(20), 2, 4, 8, 0, -1};
     // round 2, second shape sweep around 256 x 28 x 3 (pairs) -- fewer threads, more items per thread
-    case 40: return Variant{256, scale_ipt<V>(26), 3, 8, 0, 0, PF_NOBR};
-    case 41: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_NOBR};
-    case 42: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_NOBR};
-    case 43: return Variant{256, scale_ipt<V>(40), 2, 8, 0, 0, PF_NOBR};
-    case 44: return Variant{256, scale_ipt<V>(24), 3, 8, 0, 0, PF_NOBR};
-    case 45: return Variant{256, scale_ipt<V>(72), 2, 12, 0, 0, PF_NOBR};
+    case 40: return Variant{256, scale_ipt<V>(42), 2, 8, 0, 0, PF_NOBR};
+    case 41: return Variant{256, scale_ipt<V>(45), 2, 8, 0, 0, PF_NOBR};
+    case 42: return Variant{256, scale_ipt<V>(47), 2, 8, 0, 0, PF_NOBR};
+    case 43: return Variant{256, scale_ipt<V>(48), 2, 8, 0, 0, PF_NOBR};
+    case 44: return Variant{256, scale_ipt<V>(44), 2, 12, 0, 0, PF_NOBR};
+    case 45: return Variant{256, scale_ipt<V>(46), 2, 8, 0, 0, PF_NOBR};
     case 46: return Variant{256, scale_ipt<V>(36), 3, 12, 0, 0, PF_NOBR};
     case 47: return Variant{256, scale_ipt<V>(44), 2, 8, 148, 0, PF_PAIR};
     case 50: return Variant{256, scale_ipt<V>(44), 2, 8, 296, 0, PF_PAIR};
