@@ -96,6 +96,14 @@ std::atomic<bool> g_skip_constant{[] {
   const char* e = std::getenv("B2S_SKIP_CONSTANT");
   return !(e && e[0] == '0');
 }()};
+// Keys-only sorts of 1- and 2-byte keys over all their bits run as a counting sort (b2s_narrow.cu) from this many items on;
+// B2S_COUNTING_SORT=0 / b2s_set_counting_sort(0) sends them through the digit passes like every other sort (A/B runs),
+// b2s_set_counting_min_items lowers the cut-over for tests.
+std::atomic<bool> g_counting{[] {
+  const char* e = std::getenv("B2S_COUNTING_SORT");
+  return !(e && e[0] == '0');
+}()};
+std::atomic<unsigned long long> g_counting_min[2] = {{1ull << 17}, {1ull << 21}};  // [0]: 1-byte keys, [1]: 2-byte keys
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;
@@ -165,6 +173,101 @@ Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off6
   return L;
 }
 
+// Counting sort of narrow keys (b2s_narrow.cu).  The result always lands in kbuf[1]: `out` in the pointer form, the
+// alternate buffer in the DoubleBuffer form (selector flips; which buffer holds the result is "a function of the number of
+// key bits and the targeted architecture" in the reference's contract too, cub/device/device_radix_sort.cuh DoubleBuffer notes).
+bool narrow_eligible(uint64_t n, const KeyInfo& ki, int vbytes, int begin_bit, int end_bit) {
+  if (!g_counting || vbytes != 0 || ki.bytes > 2) return false;
+  if (begin_bit != 0 || end_bit != ki.bytes * 8) return false;
+  return n >= g_counting_min[ki.bytes - 1];
+}
+
+struct NarrowLayout {
+  size_t off_ctrs, off_prefix, off_zflag, off_zpartial, off_zmasks, total, zero_bytes;
+};
+NarrowLayout carve_narrow(uint64_t n, const KeyInfo& ki, bool off64) {
+  NarrowLayout L{};
+  size_t o = 0;
+  L.off_ctrs = o;    o += 256;  // 1-byte keys: completion ticket of the histogram kernel
+  L.off_prefix = o;  o += ki.bytes == 1 ? align_up((off64 ? 8 : 4) * 256, 256) : align_up(8 * 65537, 256);
+  L.off_zflag = o;   o += 256;
+  L.off_zpartial = o; o += ki.category == 2 ? 8 * 1024 : 0;
+  L.zero_bytes = o;
+  L.off_zmasks = o;  o += (ki.bytes == 2 && ki.category == 2) ? align_up(narrow_zero_mask_bytes(n), 256) : 0;  // n / 8 bytes
+  L.total = o + 255;
+  return L;
+}
+
+int narrow_sort(void* d_temp, size_t* temp_bytes, void* kbuf[2], int* selector_out, bool overwrite, uint64_t n, const KeyInfo& ki,
+                bool descending, cudaStream_t stream) {
+  const bool off64 = n >= (1ull << 30);
+  const NarrowLayout L = carve_narrow(n, ki, off64);
+  if (!d_temp) {
+    *temp_bytes = L.total;
+    return (int)cudaSuccess;
+  }
+  if (*temp_bytes < L.total) return (int)cudaErrorInvalidValue;
+  unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(d_temp), 256));
+  if (g_timing) g_events_used = 0;
+  timing_mark(stream);
+  cudaError_t e = cudaMemsetAsync(base, 0, L.zero_bytes, stream);
+  if (e != cudaSuccess) return (int)e;
+  g_last_launches++;
+  timing_mark(stream);
+
+  NarrowArgs a{};
+  a.keys_in = kbuf[0];
+  a.keys_out = kbuf[1];
+  a.n = n;
+  a.dc = make_consts(ki, descending);
+  a.kbytes = ki.bytes;
+  a.prefix = base + L.off_prefix;
+  a.prefix64 = ki.bytes == 2 || off64;
+  a.zflag = reinterpret_cast<unsigned int*>(base + L.off_zflag);
+  a.zpartial = reinterpret_cast<unsigned long long*>(base + L.off_zpartial);
+  a.zmasks = base + L.off_zmasks;
+  a.sms = sm_count();
+  auto step = [&](NarrowStep st) -> cudaError_t {
+    const cudaError_t r = narrow_step(st, a, stream);
+    if (r == cudaSuccess) {
+      g_last_launches++;
+      timing_mark(stream);
+    }
+    return r;
+  };
+  if (ki.bytes == 1) {
+    HistArgs h{};
+    h.keys = kbuf[0];
+    h.n = n;
+    h.dc = a.dc;
+    h.begin_bit = 0;
+    h.end_bit = 8;
+    h.num_passes = 1;
+    h.ghist = a.prefix;
+    h.done = reinterpret_cast<unsigned int*>(base + L.off_ctrs);
+    h.flags = nullptr;
+    h.off64 = off64;
+    const uint64_t vecs = (n + 16 * 1024 - 1) / (16 * 1024);
+    uint64_t g = (uint64_t)sm_count();
+    if (g > vecs) g = vecs ? vecs : 1;
+    h.grid = (int)g;
+    e = kernels_for(1)->hist(h, stream);
+    if (e != cudaSuccess) return (int)e;
+    g_last_launches++;
+    timing_mark(stream);
+  } else {
+    if ((e = step(NarrowStep::kHist16)) != cudaSuccess) return (int)e;
+    if ((e = step(NarrowStep::kPrefix16)) != cudaSuccess) return (int)e;
+    if (ki.category == 2 && (e = step(NarrowStep::kZeroCount)) != cudaSuccess) return (int)e;
+  }
+  if ((e = step(NarrowStep::kExpand)) != cudaSuccess) return (int)e;
+  if (ki.bytes == 2 && ki.category == 2) {
+    if ((e = step(NarrowStep::kZeroWrite)) != cudaSuccess) return (int)e;
+  }
+  if (selector_out) *selector_out = overwrite ? 1 : 0;
+  return (int)cudaSuccess;
+}
+
 // The shared implementation of both API forms.
 //   overwrite == false: pointer form  (kin -> kout, kin never written)
 //   overwrite == true : DoubleBuffer form (k[0]/k[1] ping-pong, selector returned)
@@ -198,6 +301,9 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     }
     return (int)cudaSuccess;
   }
+
+  if (narrow_eligible(n, ki, vbytes, begin_bit, end_bit))
+    return narrow_sort(d_temp, temp_bytes, kbuf, selector_out, overwrite, n, ki, descending, stream);
 
   const KernelSet* ks = kernels_for(kbytes);
   int variant = tuning_variant();
@@ -677,6 +783,19 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
 int b2s_set_single_tile(int enable) {
   const int old = b2s::g_single_tile ? 1 : 0;
   b2s::g_single_tile = enable != 0;
+  return old;
+}
+
+int b2s_set_counting_sort(int enable) {
+  const int old = b2s::g_counting ? 1 : 0;
+  b2s::g_counting = enable != 0;
+  return old;
+}
+
+uint64_t b2s_set_counting_min_items(int key_bytes, uint64_t min_items) {
+  if (key_bytes < 1 || key_bytes > 2) return 0;
+  const uint64_t old = b2s::g_counting_min[key_bytes - 1];
+  b2s::g_counting_min[key_bytes - 1] = min_items;
   return old;
 }
 

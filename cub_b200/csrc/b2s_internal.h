@@ -94,6 +94,24 @@ struct SplitArgs {
   uint64_t* counts;                  // count launch: uint64[num_splitters + 1], zeroed by the caller
 };
 
+// Counting sort of 1- and 2-byte keys without values over all their bits (b2s_narrow.cu).
+struct NarrowArgs {
+  const void* keys_in;
+  void* keys_out;     // never aliases keys_in
+  uint64_t n;
+  DigitConsts dc;
+  int kbytes;
+  void* prefix;       // 2-byte keys: uint64[65537] zeroed counts -> exclusive prefix + total; 1-byte keys: the histogram kernel's offsets
+  bool prefix64;      // element type of `prefix`
+  unsigned int* zflag;         // floating keys: device flag "both zeros occur"
+  unsigned long long* zpartial; // floating keys: uint64[1024], zero-like keys per CTA of the zero kernels
+  unsigned char* zmasks;        // floating keys: narrow_zero_mask_bytes(n) bytes, one "is +-0.0" bit per key
+  int sms;
+};
+enum class NarrowStep { kHist16, kPrefix16, kZeroCount, kExpand, kZeroWrite };
+cudaError_t narrow_step(NarrowStep step, const NarrowArgs& a, cudaStream_t s);
+size_t narrow_zero_mask_bytes(uint64_t n);
+
 // One tuning point of the digit-pass kernel.
 struct Variant {
   int nt, ipt, minb;

@@ -193,6 +193,15 @@ int b2s_variant_flow(int key_bytes, int value_bytes, int variant);
  * onesweep agent does (cub/agent/agent_radix_sort_onesweep.cuh:650-687): forward progress of the look-back then holds
  * under ANY dispatch order, at ~1.5 % of throughput.  Also B2S_TILE_CLAIM=1.  Returns the previous setting. */
 int b2s_set_tile_claim(int enable);
+/* Keys-only sorts of 1- and 2-byte keys over ALL their bits (begin_bit == 0, end_bit == key bits) run as a counting sort from
+ * a cut-over size on: joint histogram of the keys, exclusive prefix, expansion with 128-bit stores -- 2*K bytes of HBM traffic
+ * per key instead of K + 2*K*K, bit-identical results (the input order of -0.0 / +0.0 inside their common run is re-created by
+ * a stable compaction).  In the DoubleBuffer form the result is then in the ALTERNATE buffer (selector flips) whatever the
+ * number of digit passes would have been.  b2s_set_counting_sort(0) / B2S_COUNTING_SORT=0 sends those sorts through the digit
+ * passes instead; b2s_set_counting_min_items(key_bytes = 1 | 2, n) sets the cut-over (defaults 2^17 / 2^21 items).  Both
+ * return the previous setting. */
+int b2s_set_counting_sort(int enable);
+uint64_t b2s_set_counting_min_items(int key_bytes, uint64_t min_items);
 /* Tuning builds: digit pass number `pass` of every following sort writes per-tile phase timestamps (u64[tiles][16], SM clock
  * cycles; slot 0 = global timer in ns, slot 15 = SM id) to d_trace when the active variant is a trace variant.  NULL disables. */
 int b2s_set_trace(void *d_trace, int pass);
