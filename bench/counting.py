@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "counting.jsonl"))
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--max-log2", type=int, default=29)
+ap.add_argument("--min-log2", type=int, default=16)
 ap.add_argument("--steps", action="store_true")
 ap.add_argument("--keys", default="5,4,2,3,0,1", help="key type ids (tests/harness.py KEY_NAMES)")
 ap.add_argument("--tag", default="")
@@ -72,7 +73,7 @@ os.makedirs(os.path.dirname(a.out), exist_ok=True)
 with open(a.out, "a") as f:
     for kt in [int(x) for x in a.keys.split(",")]:
         nb = H.KEY_BYTES[kt]
-        sizes = [(lg, "uniform") for lg in range(16, a.max_log2 + 1, 2)] + [(a.max_log2, "uniform")]
+        sizes = [(lg, "uniform") for lg in range(a.min_log2, a.max_log2 + 1, 2)] + [(a.max_log2, "uniform")]
         sizes += [(min(28, a.max_log2), d) for d in ("and3", "const", "few")] + ([(min(28, a.max_log2), "nozero")] if kt in (4, 5) else [])
         seen = set()
         for lg, dist in sizes:

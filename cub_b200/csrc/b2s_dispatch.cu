@@ -103,7 +103,7 @@ std::atomic<bool> g_counting{[] {
   const char* e = std::getenv("B2S_COUNTING_SORT");
   return !(e && e[0] == '0');
 }()};
-std::atomic<unsigned long long> g_counting_min[2] = {{1ull << 17}, {1ull << 21}};  // [0]: 1-byte keys, [1]: 2-byte keys
+std::atomic<unsigned long long> g_counting_min[3] = {{1ull << 16}, {1ull << 22}, {1ull << 23}};  // 1-byte keys, 2-byte integers, 2-byte floats (measured cut-overs)
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;
@@ -179,20 +179,23 @@ Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off6
 bool narrow_eligible(uint64_t n, const KeyInfo& ki, int vbytes, int begin_bit, int end_bit) {
   if (!g_counting || vbytes != 0 || ki.bytes > 2) return false;
   if (begin_bit != 0 || end_bit != ki.bytes * 8) return false;
-  return n >= g_counting_min[ki.bytes - 1];
+  return n >= g_counting_min[ki.bytes == 1 ? 0 : (ki.category == 2 ? 2 : 1)];
 }
 
 struct NarrowLayout {
-  size_t off_ctrs, off_prefix, off_zflag, off_zpartial, off_zmasks, total, zero_bytes;
+  size_t off_ctrs, off_counts, off_zflag, off_zpartial, off_prefix, off_zmasks, total, zero_bytes;
 };
 NarrowLayout carve_narrow(uint64_t n, const KeyInfo& ki, bool off64) {
   NarrowLayout L{};
   size_t o = 0;
   L.off_ctrs = o;    o += 256;  // 1-byte keys: completion ticket of the histogram kernel
-  L.off_prefix = o;  o += ki.bytes == 1 ? align_up((off64 ? 8 : 4) * 256, 256) : align_up(8 * 65537, 256);
+  // 1-byte keys: the histogram kernel turns its counts into offsets in place; 2-byte keys: counts (zeroed) and prefix
+  L.off_counts = o;  o += ki.bytes == 1 ? align_up((off64 ? 8 : 4) * 256, 256) : 8 * 65536;
   L.off_zflag = o;   o += 256;
   L.off_zpartial = o; o += ki.category == 2 ? 8 * 1024 : 0;
   L.zero_bytes = o;
+  L.off_prefix = ki.bytes == 1 ? L.off_counts : o;
+  o += ki.bytes == 1 ? 0 : align_up(8 * 65537, 256);
   L.off_zmasks = o;  o += (ki.bytes == 2 && ki.category == 2) ? align_up(narrow_zero_mask_bytes(n), 256) : 0;  // n / 8 bytes
   L.total = o + 255;
   return L;
@@ -221,6 +224,7 @@ int narrow_sort(void* d_temp, size_t* temp_bytes, void* kbuf[2], int* selector_o
   a.n = n;
   a.dc = make_consts(ki, descending);
   a.kbytes = ki.bytes;
+  a.counts = base + L.off_counts;
   a.prefix = base + L.off_prefix;
   a.prefix64 = ki.bytes == 2 || off64;
   a.zflag = reinterpret_cast<unsigned int*>(base + L.off_zflag);
@@ -796,6 +800,7 @@ uint64_t b2s_set_counting_min_items(int key_bytes, uint64_t min_items) {
   if (key_bytes < 1 || key_bytes > 2) return 0;
   const uint64_t old = b2s::g_counting_min[key_bytes - 1];
   b2s::g_counting_min[key_bytes - 1] = min_items;
+  if (key_bytes == 2) b2s::g_counting_min[2] = min_items;  // floating 2-byte keys follow (their own default is higher)
   return old;
 }
 

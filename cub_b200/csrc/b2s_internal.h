@@ -101,7 +101,8 @@ struct NarrowArgs {
   uint64_t n;
   DigitConsts dc;
   int kbytes;
-  void* prefix;       // 2-byte keys: uint64[65537] zeroed counts -> exclusive prefix + total; 1-byte keys: the histogram kernel's offsets
+  void* counts;       // 2-byte keys: uint64[65536] joint histogram, zeroed by the caller
+  void* prefix;       // 2-byte keys: uint64[65537] exclusive prefix + total; 1-byte keys: the histogram kernel's offsets
   bool prefix64;      // element type of `prefix`
   unsigned int* zflag;         // floating keys: device flag "both zeros occur"
   unsigned long long* zpartial; // floating keys: uint64[1024], zero-like keys per CTA of the zero kernels

@@ -35,10 +35,13 @@ constexpr int NH_UNROLL = 4;
 // of keys: CTA 2c counts the images with a clear top bit, CTA 2c+1 the others (the second reader of a line hits L2).
 // The image transform runs on two packed keys at a time; the pair's half is folded into the XOR constant so that
 // "mine" is bit 15 / bit 31 of the transformed word.
-template <bool IS_FLOAT, bool PLAIN>
+template <bool IS_FLOAT, int MODE>
 __global__ void __launch_bounds__(NH_THREADS, 1) joint_hist16_kernel(const uint16_t* __restrict__ keys, unsigned long long n,
                                                                    unsigned int xor16, unsigned long long* __restrict__ gbins) {
   extern __shared__ __align__(16) unsigned int nh_bins[];
+  __shared__ unsigned int nh_dummy[NH_THREADS];
+  constexpr bool NOBR = (MODE & 1) != 0;  // every lane issues the atomic: keys of the other half add to a private word (bank == lane)
+  constexpr bool PREF = (MODE & 2) != 0;  // the next batch of loads is issued before the current one is counted
   const int tid = threadIdx.x;
   const unsigned int half = blockIdx.x & 1u;
   const unsigned int chunk = blockIdx.x >> 1, chunks = gridDim.x >> 1;
@@ -47,8 +50,8 @@ __global__ void __launch_bounds__(NH_THREADS, 1) joint_hist16_kernel(const uint1
   const unsigned int bins_s = smem_u32(nh_bins);
   const unsigned int x1 = (xor16 & 0xffffu) ^ (half ? 0u : 0x8000u);
   const unsigned int x2 = x1 | (x1 << 16);
-  // PLAIN: the increment is hidden from the compiler, which otherwise emits the warp-aggregating ATOMS.POPC.INC form
-  const unsigned int one = PLAIN ? opaque(1u) : 1u;
+  // MODE bit 2: one dummy word per warp (all lanes of the other half on ONE address) instead of one per lane
+  const unsigned int dummy_s = smem_u32(nh_dummy + ((MODE & 4) ? (tid & ~31) : tid));
   auto count_word = [&](unsigned int w) {
     unsigned int t;
     if (IS_FLOAT) {
@@ -57,8 +60,21 @@ __global__ void __launch_bounds__(NH_THREADS, 1) joint_hist16_kernel(const uint1
     } else {
       t = w ^ x2;
     }
-    if (t & 0x8000u) red_shared_add(bins_s + ((t & 0x7fffu) << 2), one);
-    if (t & 0x80000000u) red_shared_add(bins_s + ((t >> 14) & 0x1fffcu), one);
+    if (NOBR) {
+      // ptxas wraps a predicated shared-memory atomic into BSSY / BRA / ATOMS / BSYNC (6 of 23 instructions per 32 keys and
+      // the top stall reason, branch resolving); an unconditional one on a select of two addresses has no branch
+      red_shared_add((t & 0x8000u) ? bins_s + ((t & 0x7fffu) << 2) : dummy_s, 1u);
+      red_shared_add((t & 0x80000000u) ? bins_s + ((t >> 14) & 0x1fffcu) : dummy_s, 1u);
+    } else {
+      if (t & 0x8000u) red_shared_add(bins_s + ((t & 0x7fffu) << 2), 1u);
+      if (t & 0x80000000u) red_shared_add(bins_s + ((t >> 14) & 0x1fffcu), 1u);
+    }
+  };
+  auto count_vec = [&](const uint4& q) {
+    count_word(q.x);
+    count_word(q.y);
+    count_word(q.z);
+    count_word(q.w);
   };
 
   const uintptr_t addr = reinterpret_cast<uintptr_t>(keys);
@@ -85,25 +101,38 @@ __global__ void __launch_bounds__(NH_THREADS, 1) joint_hist16_kernel(const uint1
   const uint4* vec = reinterpret_cast<const uint4*>(keys + head);
   const unsigned long long stride = (unsigned long long)chunks * NH_THREADS;
   unsigned long long v = (unsigned long long)chunk * NH_THREADS + tid;
-  for (; v + (NH_UNROLL - 1) * stride < nvec; v += NH_UNROLL * stride) {
+  if (PREF) {
     uint4 q[NH_UNROLL];
+    bool have = v + (NH_UNROLL - 1) * stride < nvec;
+    if (have) {
 #pragma unroll
-    for (int j = 0; j < NH_UNROLL; ++j) q[j] = __ldg(vec + v + j * stride);
+      for (int j = 0; j < NH_UNROLL; ++j) q[j] = __ldg(vec + v + j * stride);
+    }
+    while (have) {
+      const unsigned long long vn = v + NH_UNROLL * stride;
+      const bool have_next = vn + (NH_UNROLL - 1) * stride < nvec;
+      uint4 qn[NH_UNROLL];
+      if (have_next) {
 #pragma unroll
-    for (int j = 0; j < NH_UNROLL; ++j) {
-      count_word(q[j].x);
-      count_word(q[j].y);
-      count_word(q[j].z);
-      count_word(q[j].w);
+        for (int j = 0; j < NH_UNROLL; ++j) qn[j] = __ldg(vec + vn + j * stride);
+      }
+#pragma unroll
+      for (int j = 0; j < NH_UNROLL; ++j) count_vec(q[j]);
+#pragma unroll
+      for (int j = 0; j < NH_UNROLL; ++j) q[j] = qn[j];
+      v = vn;
+      have = have_next;
+    }
+  } else {
+    for (; v + (NH_UNROLL - 1) * stride < nvec; v += NH_UNROLL * stride) {
+      uint4 q[NH_UNROLL];
+#pragma unroll
+      for (int j = 0; j < NH_UNROLL; ++j) q[j] = __ldg(vec + v + j * stride);
+#pragma unroll
+      for (int j = 0; j < NH_UNROLL; ++j) count_vec(q[j]);
     }
   }
-  for (; v < nvec; v += stride) {
-    const uint4 q = __ldg(vec + v);
-    count_word(q.x);
-    count_word(q.y);
-    count_word(q.z);
-    count_word(q.w);
-  }
+  for (; v < nvec; v += stride) count_vec(__ldg(vec + v));
   __syncthreads();
   unsigned long long* mine = gbins + (size_t)half * NH_HALF;
   for (int i = tid; i < NH_HALF; i += NH_THREADS) {
@@ -113,56 +142,37 @@ __global__ void __launch_bounds__(NH_THREADS, 1) joint_hist16_kernel(const uint1
 }
 
 // counts of the 65536 images -> exclusive prefix (+ total at [65536]); floating keys: flag "both zeros occur".
-// ONE 1024-thread CTA; four rounds of 16384 counts staged in shared memory (coalesced in, thread-blocked scan with a
-// padded layout, coalesced out) -- a thread-blocked scan straight on global memory is bound by 64 dependent L2 round trips.
-constexpr int SC_CHUNK = 16384;
-constexpr int SC_PER = SC_CHUNK / 1024;
-constexpr size_t SC_SMEM = (size_t)(SC_CHUNK + SC_CHUNK / 16) * 8;
-__global__ void __launch_bounds__(1024, 1) prefix16_kernel(unsigned long long* __restrict__ bins, unsigned int* __restrict__ zflag) {
-  extern __shared__ __align__(16) unsigned long long sc[];
-  __shared__ unsigned long long s_warp[32];
+// 64 CTAs of 1024 images; CTA c first sums the counts of ALL images before its own (c * 8 KB of L2-resident reads, all
+// independent) and then scans its own 1024 -- no ordering between CTAs, which is why the prefix is a second array.
+constexpr int PX_CTAS = 64;
+__global__ void __launch_bounds__(1024) prefix16_kernel(const unsigned long long* __restrict__ counts,
+                                                        unsigned long long* __restrict__ prefix, unsigned int* __restrict__ zflag) {
+  __shared__ unsigned long long s_warp[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (zflag != nullptr && tid == 0) *zflag = (bins[0x7fff] != 0 && bins[0x8000] != 0) ? 1u : 0u;  // read before round 1 / 2 rewrite them
-  __syncthreads();
-  auto pad = [](int i) { return i + (i >> 4); };
-  unsigned long long carry = 0;
-  for (int chunk = 0; chunk < 65536 / SC_CHUNK; ++chunk) {
-    unsigned long long* g = bins + (size_t)chunk * SC_CHUNK;
+  if (zflag != nullptr && blockIdx.x == 0 && tid == 0) *zflag = (counts[0x7fff] != 0 && counts[0x8000] != 0) ? 1u : 0u;
+  unsigned long long before = 0;
+#pragma unroll 8
+  for (unsigned int c = 0; c < blockIdx.x; ++c) before += __ldcg(counts + c * 1024 + tid);
+  const unsigned long long mine = __ldcg(counts + blockIdx.x * 1024 + tid);
+  unsigned long long incl = mine;
 #pragma unroll
-    for (int j = 0; j < SC_PER; ++j) sc[pad(j * 1024 + tid)] = __ldcg(g + j * 1024 + tid);
-    __syncthreads();
-    unsigned long long sum = 0;
-#pragma unroll
-    for (int j = 0; j < SC_PER; ++j) sum += sc[pad(tid * SC_PER + j)];
-    unsigned long long incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned long long base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 32; ++w) {
-      const unsigned long long t = s_warp[w];
-      if (w < warp) base += t;
-      total += t;
-    }
-    unsigned long long run = carry + base + incl - sum;
-#pragma unroll
-    for (int j = 0; j < SC_PER; ++j) {
-      const unsigned long long c = sc[pad(tid * SC_PER + j)];  // re-read rather than 16 values held across the barrier
-      sc[pad(tid * SC_PER + j)] = run;
-      run += c;
-    }
-    carry += total;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < SC_PER; ++j) g[j * 1024 + tid] = sc[pad(j * 1024 + tid)];
-    __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-  if (tid == 0) bins[65536] = carry;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 31) s_warp[0][warp] = incl;
+  if (lane == 0) s_warp[1][warp] = before;
+  __syncthreads();
+  unsigned long long base = 0;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) {
+    base += s_warp[1][w];
+    if (w < warp) base += s_warp[0][w];
+  }
+  prefix[blockIdx.x * 1024 + tid] = base + incl - mine;
+  if (blockIdx.x == PX_CTAS - 1 && tid == 1023) prefix[65536] = base + incl;
 }
 
 // ---- floating zeros: stable compaction of the zero-like input keys into their run of the output --------------------
@@ -437,7 +447,8 @@ size_t narrow_zero_mask_bytes(uint64_t n) { return (size_t)((n / 8 + Z_TILE_VECS
 
 cudaError_t narrow_step(NarrowStep step, const NarrowArgs& a, cudaStream_t s) {
   const uint16_t* k16 = reinterpret_cast<const uint16_t*>(a.keys_in);
-  unsigned long long* bins = reinterpret_cast<unsigned long long*>(a.prefix);
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(a.prefix);      // exclusive prefix (what the later steps read)
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(a.counts);  // 2-byte keys: the joint histogram
   const bool fl = a.dc.is_float;
   // CTAs of the two zero kernels (they must agree): four per SM, at most one per tile
   auto zero_grid = [&]() -> unsigned int {
@@ -449,30 +460,30 @@ cudaError_t narrow_step(NarrowStep step, const NarrowArgs& a, cudaStream_t s) {
   };
   switch (step) {
     case NarrowStep::kHist16: {
-      static const bool plain = [] {
-        const char* e = std::getenv("B2S_NH_PLAIN");
-        return e && e[0] == '1';
+      static const int mode = [] {  // A/B switch of the histogram's inner loop (see joint_hist16_kernel)
+        const char* e = std::getenv("B2S_NH_MODE");
+        return e ? (std::atoi(e) & 7) : 5;
       }();
       const size_t smem = (size_t)NH_HALF * 4;
       using Kern = void (*)(const uint16_t*, unsigned long long, unsigned int, unsigned long long*);
-      const Kern table[4] = {joint_hist16_kernel<false, false>, joint_hist16_kernel<false, true>,
-                             joint_hist16_kernel<true, false>, joint_hist16_kernel<true, true>};
-      const Kern kern = table[(fl ? 2 : 0) + (plain ? 1 : 0)];
+      const Kern table[12] = {joint_hist16_kernel<false, 0>, joint_hist16_kernel<false, 1>, joint_hist16_kernel<false, 2>,
+                              joint_hist16_kernel<false, 3>, joint_hist16_kernel<false, 5>, joint_hist16_kernel<false, 7>,
+                              joint_hist16_kernel<true, 0>,  joint_hist16_kernel<true, 1>,  joint_hist16_kernel<true, 2>,
+                              joint_hist16_kernel<true, 3>,  joint_hist16_kernel<true, 5>,  joint_hist16_kernel<true, 7>};
+      const int slot = mode < 4 ? mode : (mode == 5 ? 4 : (mode == 7 ? 5 : 1));
+      const Kern kern = table[(fl ? 6 : 0) + slot];
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       // pairs of CTAs; no more pairs than 16 KB chunks of keys
       uint64_t pairs = (uint64_t)(a.sms / 2 > 0 ? a.sms / 2 : 1);
       const uint64_t chunks = (a.n * 2 + 16 * 1024 - 1) / (16 * 1024);
       if (pairs > chunks) pairs = chunks ? chunks : 1;
-      kern<<<(unsigned int)(2 * pairs), NH_THREADS, smem, s>>>(k16, a.n, (unsigned int)a.dc.xor_mask, bins);
+      kern<<<(unsigned int)(2 * pairs), NH_THREADS, smem, s>>>(k16, a.n, (unsigned int)a.dc.xor_mask, counts);
       return cudaGetLastError();
     }
-    case NarrowStep::kPrefix16: {
-      cudaError_t e = cudaFuncSetAttribute(prefix16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
-      if (e != cudaSuccess) return e;
-      prefix16_kernel<<<1, 1024, SC_SMEM, s>>>(bins, fl ? a.zflag : nullptr);
+    case NarrowStep::kPrefix16:
+      prefix16_kernel<<<PX_CTAS, 1024, 0, s>>>(counts, bins, fl ? a.zflag : nullptr);
       return cudaGetLastError();
-    }
     case NarrowStep::kZeroCount:
       zero_count16_kernel<<<zero_grid(), Z_THREADS, 0, s>>>(k16, a.n, a.zflag, a.zpartial, a.zmasks);
       return cudaGetLastError();

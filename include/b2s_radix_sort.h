@@ -198,7 +198,7 @@ int b2s_set_tile_claim(int enable);
  * per key instead of K + 2*K*K, bit-identical results (the input order of -0.0 / +0.0 inside their common run is re-created by
  * a stable compaction).  In the DoubleBuffer form the result is then in the ALTERNATE buffer (selector flips) whatever the
  * number of digit passes would have been.  b2s_set_counting_sort(0) / B2S_COUNTING_SORT=0 sends those sorts through the digit
- * passes instead; b2s_set_counting_min_items(key_bytes = 1 | 2, n) sets the cut-over (defaults 2^17 / 2^21 items).  Both
+ * passes instead; b2s_set_counting_min_items(key_bytes = 1 | 2, n) sets the cut-over (defaults: 2^16 items for 1-byte keys, 2^22 for 2-byte integers, 2^23 for f16 / bf16 -- where the counting path overtakes the digit passes on a B200; setting key_bytes = 2 sets both 2-byte cut-overs).  Both
  * return the previous setting. */
 int b2s_set_counting_sort(int enable);
 uint64_t b2s_set_counting_min_items(int key_bytes, uint64_t min_items);
