@@ -20,6 +20,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "b2s_common.cuh"
 #include "b2s_internal.h"
@@ -472,8 +475,19 @@ cudaError_t narrow_step(NarrowStep step, const NarrowArgs& a, cudaStream_t s) {
                               joint_hist16_kernel<true, 3>,  joint_hist16_kernel<true, 5>,  joint_hist16_kernel<true, 7>};
       const int slot = mode < 4 ? mode : (mode == 5 ? 4 : (mode == 7 ? 5 : 1));
       const Kern kern = table[(fl ? 6 : 0) + slot];
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
+      {  // opt in to 128 KB of dynamic shared memory once per (kernel, device)
+        static std::mutex mu;
+        static std::set<std::pair<const void*, int>> done;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), dev);
+        std::lock_guard<std::mutex> lock(mu);
+        if (!done.count(key)) {
+          const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+          done.insert(key);
+        }
+      }
       // pairs of CTAs; no more pairs than 16 KB chunks of keys
       uint64_t pairs = (uint64_t)(a.sms / 2 > 0 ? a.sms / 2 : 1);
       const uint64_t chunks = (a.n * 2 + 16 * 1024 - 1) / (16 * 1024);

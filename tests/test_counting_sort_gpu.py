@@ -175,3 +175,66 @@ def test_default_cut_over_vs_reference_cub_and_digit_passes(b2s, refcub, kt, lg)
             b2s.b2s_set_counting_sort(old)
         assert torch.equal(k_cnt, k_ref), "counting path differs from reference CUB"
         assert torch.equal(k_dig, k_ref), "digit passes differ from reference CUB"
+
+
+@pytest.mark.parametrize("kt", [5, 2, 0])
+def test_cuda_graph_capture_and_replay_of_the_counting_path(counting_everywhere, oracle, kt):
+    """The counting path is stream-ordered work only (memset + kernels, device-side decisions about the zeros): captured once,
+    the graph must sort whatever is in the input buffer at replay time -- including inputs whose zero flag differs."""
+    b2s = counting_everywhere
+    nb = H.KEY_BYTES[kt]
+    n = 300_001
+    rng = np.random.default_rng(kt)
+    keys = torch.zeros(n, dtype=H.CONTAINER[nb], device="cuda")
+    out = torch.empty_like(keys)
+    import ctypes
+    nbytes = ctypes.c_size_t(0)
+    args = (H._p(keys), H._p(out), None, None, n, kt, 0, 4, 1, 0, 8 * nb)
+    assert b2s.b2s_radix_sort(None, ctypes.byref(nbytes), *args, None) == 0
+    temp = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        assert b2s.b2s_radix_sort(ctypes.c_void_p(temp.data_ptr()), ctypes.byref(nbytes), *args, ctypes.c_void_p(s.cuda_stream)) == 0
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        assert b2s.b2s_radix_sort(ctypes.c_void_p(temp.data_ptr()), ctypes.byref(nbytes), *args,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    for rep in range(4):
+        raw = H.random_bits(rng, n, nb)
+        if kt == 5:
+            raw = H.spice_floats(raw, nb) if rep % 2 == 0 else (raw | np.uint16(1))  # both zeros / no zero at all
+        keys.copy_(H.to_dev(raw))
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        ek, _ = oracle.radix_sort(raw, None, kt, True)
+        assert np.array_equal(H.to_np(out, raw.dtype), ek), f"graph replay {rep}"
+
+
+def test_concurrent_streams_share_nothing(counting_everywhere, oracle):
+    """Several counting sorts in flight on different streams with their own temp storage."""
+    b2s = counting_everywhere
+    import ctypes
+    rng = np.random.default_rng(77)
+    jobs = []
+    for i, kt in enumerate([5, 4, 2, 3, 0, 1, 5, 2]):
+        nb = H.KEY_BYTES[kt]
+        n = 150_000 + 1111 * i
+        raw = H.random_bits(rng, n, nb)
+        if kt in (4, 5):
+            raw = H.spice_floats(raw, nb)
+        keys, out = H.to_dev(raw), torch.empty(n, dtype=H.CONTAINER[nb], device="cuda")
+        nbytes = ctypes.c_size_t(0)
+        args = (H._p(keys), H._p(out), None, None, n, kt, 0, 4, i & 1, 0, 8 * nb)
+        assert b2s.b2s_radix_sort(None, ctypes.byref(nbytes), *args, None) == 0
+        temp = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+        jobs.append((kt, raw, keys, out, temp, nbytes, args, torch.cuda.Stream(), bool(i & 1)))
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for kt, raw, keys, out, temp, nbytes, args, st, desc in jobs:
+            assert b2s.b2s_radix_sort(ctypes.c_void_p(temp.data_ptr()), ctypes.byref(nbytes), *args, ctypes.c_void_p(st.cuda_stream)) == 0
+    torch.cuda.synchronize()
+    for kt, raw, keys, out, temp, nbytes, args, st, desc in jobs:
+        ek, _ = oracle.radix_sort(raw, None, kt, desc)
+        assert np.array_equal(H.to_np(out, raw.dtype), ek), H.KEY_NAMES[kt]
