@@ -463,18 +463,23 @@ cudaError_t narrow_step(NarrowStep step, const NarrowArgs& a, cudaStream_t s) {
   };
   switch (step) {
     case NarrowStep::kHist16: {
-      static const int mode = [] {  // A/B switch of the histogram's inner loop (see joint_hist16_kernel)
+      const size_t smem = (size_t)NH_HALF * 4;
+      using Kern = void (*)(const uint16_t*, unsigned long long, unsigned int, unsigned long long*);
+#ifdef B2S_TUNING
+      // tuning library only: A/B switch of the histogram's inner loop (MODE bits at joint_hist16_kernel; bench/runs/counting_modes.sh)
+      static const int mode = [] {
         const char* e = std::getenv("B2S_NH_MODE");
         return e ? (std::atoi(e) & 7) : 5;
       }();
-      const size_t smem = (size_t)NH_HALF * 4;
-      using Kern = void (*)(const uint16_t*, unsigned long long, unsigned int, unsigned long long*);
       const Kern table[12] = {joint_hist16_kernel<false, 0>, joint_hist16_kernel<false, 1>, joint_hist16_kernel<false, 2>,
                               joint_hist16_kernel<false, 3>, joint_hist16_kernel<false, 5>, joint_hist16_kernel<false, 7>,
                               joint_hist16_kernel<true, 0>,  joint_hist16_kernel<true, 1>,  joint_hist16_kernel<true, 2>,
                               joint_hist16_kernel<true, 3>,  joint_hist16_kernel<true, 5>,  joint_hist16_kernel<true, 7>};
       const int slot = mode < 4 ? mode : (mode == 5 ? 4 : (mode == 7 ? 5 : 1));
       const Kern kern = table[(fl ? 6 : 0) + slot];
+#else
+      const Kern kern = fl ? joint_hist16_kernel<true, 5> : joint_hist16_kernel<false, 5>;  // branch-free atomics, one dummy word per warp
+#endif
       {  // opt in to 128 KB of dynamic shared memory once per (kernel, device)
         static std::mutex mu;
         static std::set<std::pair<const void*, int>> done;
