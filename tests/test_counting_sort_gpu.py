@@ -238,3 +238,33 @@ def test_concurrent_streams_share_nothing(counting_everywhere, oracle):
     for kt, raw, keys, out, temp, nbytes, args, st, desc in jobs:
         ek, _ = oracle.radix_sort(raw, None, kt, desc)
         assert np.array_equal(H.to_np(out, raw.dtype), ek), H.KEY_NAMES[kt]
+
+
+def test_python_mirror_and_frontend_reach_the_counting_path(b2s, oracle):
+    """cub_b200.sort_keys / DeviceRadixSort.SortKeys(DoubleBuffer) on torch bf16 / int16 / uint8 tensors above the default
+    cut-over: same bits as the oracle; the DoubleBuffer's Current() names the result."""
+    import cub_b200 as cb
+
+    rng = np.random.default_rng(2026)
+    for dtype, kt, n in ((torch.bfloat16, 5, (1 << 23) + 13), (torch.int16, 3, (1 << 22) + 7), (torch.uint8, 0, (1 << 17) + 3)):
+        nb = H.KEY_BYTES[kt]
+        raw = H.random_bits(rng, n, nb)
+        if kt == 5:
+            raw = H.spice_floats(raw, nb)
+        t = H.to_dev(raw).view(dtype)
+        for desc in (False, True):
+            out = cb.sort_keys(t, descending=desc)
+            torch.cuda.synchronize()
+            ek, _ = oracle.radix_sort(raw, None, kt, desc)
+            assert np.array_equal(H.to_np(out.view(H.CONTAINER[nb]), raw.dtype), ek), (dtype, desc)
+        db = cb.DoubleBuffer(t.clone(), torch.empty_like(t))
+        fn = cb.DeviceRadixSort.SortKeys
+        err, nbytes = fn(None, 0, db, n)
+        assert err == 0
+        temp = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        err, _ = fn(temp, nbytes, db, n)
+        assert err == 0
+        torch.cuda.synchronize()
+        ek, _ = oracle.radix_sort(raw, None, kt, False)
+        assert db.selector == 1
+        assert np.array_equal(H.to_np(db.Current().view(H.CONTAINER[nb]), raw.dtype), ek), dtype
