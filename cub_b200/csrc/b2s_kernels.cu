@@ -31,7 +31,7 @@ constexpr int K = B2S_K;
 // laboratory kernel (b2s_onesweep.cuh).  Table entries give items/thread for 4-byte keys with <=4-byte values; wider
 // items scale it down by bytes (shared memory) and by registers.
 #ifdef B2S_TUNING
-constexpr int NUM_VARIANTS = 52;
+constexpr int NUM_VARIANTS = 58;
 #else
 constexpr int NUM_VARIANTS = 1;
 #endif
@@ -145,6 +145,13 @@ constexpr Variant variant_cfg(int vi) {
     case 51: return Variant{256, scale_ipt<V>(56), 3, 12, 0, 0, PF_NOBR};
     case 48: return Variant{256, scale_ipt<V>(48), 3, 12, 0, 0, PF_NOBR};
     case 49: return Variant{256, scale_ipt<V>(60), 2, 12, 0, 0, PF_NOBR};
+    // wave balance at mid sizes (keys alone, 3 CTAs/SM: 444 slots): tile sizes that fill whole waves at 2^24 keys
+    case 52: return Variant{256, scale_ipt<V>(50), 3, 8, 0, 0, PF_NOBR};
+    case 53: return Variant{256, scale_ipt<V>(52), 3, 8, 0, 0, PF_NOBR};
+    case 54: return Variant{256, scale_ipt<V>(38), 3, 8, 0, 0, PF_NOBR};
+    case 55: return Variant{256, scale_ipt<V>(40), 3, 8, 0, 0, PF_NOBR};
+    case 56: return Variant{256, scale_ipt<V>(30), 3, 8, 0, 0, PF_NOBR};
+    case 57: return Variant{256, scale_ipt<V>(44), 3, 8, 0, 0, PF_NOBR};
     default: return d;
   }
 #else
