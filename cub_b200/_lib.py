@@ -66,6 +66,7 @@ EXPORTS = {
     "b2s_variant_flow": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int]),
     "b2s_set_tile_claim": (_c.c_int, [_c.c_int]),
     "b2s_set_counting_sort": (_c.c_int, [_c.c_int]),
+    "b2s_set_float_zero_recording": (_c.c_int, [_c.c_int]),
     "b2s_set_counting_min_items": (_c.c_uint64, [_c.c_int, _c.c_uint64]),
     "b2s_set_trace": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "b2s_set_single_tile": (_c.c_int, [_c.c_int]),

@@ -104,6 +104,13 @@ std::atomic<bool> g_counting{[] {
   return !(e && e[0] == '0');
 }()};
 std::atomic<unsigned long long> g_counting_min[3] = {{1ull << 16}, {1ull << 22}, {1ull << 23}};  // 1-byte keys, 2-byte integers, 2-byte floats (measured cut-overs)
+// Full-range sorts of 4- / 8-byte floating keys (no values or 4-byte values) record their zeros in the first pass and restore
+// them after the last one (b2s_fzero.cu); B2S_FLOAT_ZERO_RECORD=0 / b2s_set_float_zero_recording(0) keeps the zero collapse in
+// every digit extraction instead (A/B runs).
+std::atomic<bool> g_fzero{[] {
+  const char* e = std::getenv("B2S_FLOAT_ZERO_RECORD");
+  return !(e && e[0] == '0');
+}()};
 // Tuning hook: phase-timestamp buffer for the trace variants of the digit pass (MODE bit 4), one pass per sort.
 unsigned long long* g_trace = nullptr;
 int g_trace_pass = -1;
@@ -155,9 +162,10 @@ int sm_count() {
 struct Layout {
   size_t off_ctrs, off_hist, off_status0, off_status1, off_keys, off_vals, total;
   size_t zero_bytes;  // [off_ctrs, off_ctrs + zero_bytes) is cleared once per sort
+  size_t off_fz_z, off_fz_s, off_fz_partial;  // zero recording (b2s_fzero.cu), when used
 };
 
-Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off64, bool need_alt) {
+Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off64, bool need_alt, bool fz = false) {
   Layout L{};
   const size_t osz = off64 ? 8 : 4;
   const uint64_t tiles = (n + tile - 1) / tile;
@@ -169,6 +177,10 @@ Layout carve(uint64_t n, int kbytes, int vbytes, int passes, int tile, bool off6
   L.off_status1 = o;   o += passes > 1 ? align_up(osz * 256 * tiles, 256) : 0;
   L.off_keys = o;      o += need_alt ? align_up((size_t)n * kbytes, 256) : 0;
   L.off_vals = o;      o += (need_alt && vbytes) ? align_up((size_t)n * vbytes, 256) : 0;
+  const size_t fzw = fz ? align_up(fzero_plane_words(n) * 4, 256) : 0;
+  L.off_fz_z = o;      o += fzw;
+  L.off_fz_s = o;      o += fzw;
+  L.off_fz_partial = o; o += fz ? 8 * 1024 : 0;
   L.total = o + 255;   // slack so any d_temp_storage alignment works
   return L;
 }
@@ -314,9 +326,12 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
   if (variant < 0 || variant >= ks->num_variants()) variant = 0;
   const int passes = (num_bits + 7) / 8;
   const bool off64 = n >= (1ull << 30);
-  const int tile = ks->tile(variant, vbytes, ki.category == 2, off64);
+  // zero recording: floating keys, every bit sorted -- the zeros' run is then found at digit 0x80 of the top pass
+  const bool fz = g_fzero && ki.category == 2 && kbytes >= 4 && (vbytes == 0 || vbytes == 4) && begin_bit == 0 &&
+                  end_bit == kbytes * 8 && passes >= 2;
+  const int tile = ks->tile(variant, vbytes, ki.category == 2 && !fz, off64);  // recording sorts run on the integer shapes
   const bool need_alt = !overwrite && passes > 1;
-  const Layout L = carve(n, kbytes, vbytes, passes, tile, off64, need_alt);
+  const Layout L = carve(n, kbytes, vbytes, passes, tile, off64, need_alt, fz);
 
   if (!d_temp) {
     *temp_bytes = L.total;
@@ -405,23 +420,31 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
       vdst = vbytes ? (to_out ? vbuf[1] : vtmp) : nullptr;
     }
     PassArgs a{};
+    const bool fpass = fz && (p == 0 || p == passes - 1);  // first / last pass convert (and record): ImageFloatOp kernels
     a.keys_in = ksrc;
     a.keys_out = kdst;
     a.vals_in = vsrc;
     a.vals_out = vdst;
+    a.zero_z = fpass ? reinterpret_cast<unsigned int*>(base + L.off_fz_z) : nullptr;
+    a.zero_s = fpass ? reinterpret_cast<unsigned int*>(base + L.off_fz_s) : nullptr;
     a.status = status[p & 1];
     a.status_next = (p + 1 < passes) ? status[(p + 1) & 1] : nullptr;
     a.bins = hist + osz * 256 * (size_t)p;
     a.tile_counter = ctrs + 1 + p;
     a.n = n;
     a.dc = dc;
+    if (fz && !fpass) {  // between the first and the last pass the keys are plain bit-ordered integers
+      a.dc = DigitConsts{};
+      a.dc.pad_key = kbytes == 8 ? ~0ull : 0xffffffffull;
+    }
     a.bit = begin_bit + 8 * p;
     a.nbits = (end_bit - a.bit) < 8 ? (end_bit - a.bit) : 8;
     a.off64 = off64;
     a.vbytes = vbytes;
     a.trace = (g_trace_pass == p) ? g_trace : nullptr;
     a.claim = g_claim;
-    a.skip_flag = g_skip_constant ? ctrs + 1 + passes + p : nullptr;
+    // the recording pass has to see every key: no constant-digit copy for it
+    a.skip_flag = (g_skip_constant && !(fz && p == 0)) ? ctrs + 1 + passes + p : nullptr;
     a.raw_in = p == 0;
     a.raw_out = p == passes - 1;
     e = ks->onesweep(variant, a, stream);
@@ -431,6 +454,24 @@ int sort_impl(void* d_temp, size_t* temp_bytes, void* kbuf[2], void* vbuf[2], in
     ksrc = kdst;
     vsrc = vdst;
     cur ^= 1;
+  }
+  if (fz) {  // the zeros arrived as one run of equal keys in input order: give them their recorded signs back
+    FzeroArgs f{};
+    f.zero_z = reinterpret_cast<const unsigned int*>(base + L.off_fz_z);
+    f.zero_s = reinterpret_cast<const unsigned int*>(base + L.off_fz_s);
+    f.n = n;
+    f.kbytes = kbytes;
+    f.keys_out = const_cast<void*>(ksrc);
+    f.top_bins = hist + osz * 256 * (size_t)(passes - 1);
+    f.off64 = off64;
+    f.partial = reinterpret_cast<unsigned long long*>(base + L.off_fz_partial);
+    f.sms = sm_count();
+    if ((e = fzero_count_launch(f, stream)) != cudaSuccess) return (int)e;
+    g_last_launches++;
+    timing_mark(stream);
+    if ((e = fzero_write_launch(f, stream)) != cudaSuccess) return (int)e;
+    g_last_launches++;
+    timing_mark(stream);
   }
   if (selector_out) *selector_out = overwrite ? cur : 0;
   return (int)cudaSuccess;
@@ -787,6 +828,12 @@ int b2s_describe_variant(int key_bytes, int value_bytes, int variant, int* nt, i
 int b2s_set_single_tile(int enable) {
   const int old = b2s::g_single_tile ? 1 : 0;
   b2s::g_single_tile = enable != 0;
+  return old;
+}
+
+int b2s_set_float_zero_recording(int enable) {
+  const int old = b2s::g_fzero ? 1 : 0;
+  b2s::g_fzero = enable != 0;
   return old;
 }
 

@@ -46,6 +46,10 @@ struct PassArgs {
   bool claim;                 // tile ids from an atomic ticket instead of the block index (see b2s_set_tile_claim)
   const unsigned int* skip_flag;  // DEVICE flag written by the histogram kernel: non-zero = every key has the same digit in this pass
   bool raw_in, raw_out;       // floating keys: this pass reads / writes the raw encoding (first / last pass); images in between
+  // zero recording (full-range sorts of 4- / 8-byte floating keys, b2s_fzero.cu): non-null selects the ImageFloatOp kernels for
+  // this pass; the first pass writes one word per 32 input keys to each plane
+  unsigned int* zero_z;
+  unsigned int* zero_s;
 };
 
 // Whole sort of one small tile in a single launch (b2s_single_tile.cuh).
@@ -112,6 +116,23 @@ struct NarrowArgs {
 enum class NarrowStep { kHist16, kPrefix16, kZeroCount, kExpand, kZeroWrite };
 cudaError_t narrow_step(NarrowStep step, const NarrowArgs& a, cudaStream_t s);
 size_t narrow_zero_mask_bytes(uint64_t n);
+
+// Zero recording for full-range sorts of 4- / 8-byte floating keys (b2s_fzero.cu): after the last digit pass the run of zeros
+// [offset of digit 0x80 in the top pass, + number of zeros) of the output gets the recorded sign bits back, in input order.
+struct FzeroArgs {
+  const unsigned int* zero_z;   // planes written by the first digit pass
+  const unsigned int* zero_s;
+  uint64_t n;
+  int kbytes;
+  void* keys_out;               // final output of the sort (raw encoding)
+  const void* top_bins;         // OffT[256]: exclusive digit offsets of the top pass
+  bool off64;
+  unsigned long long* partial;  // uint64[1024]
+  int sms;
+};
+cudaError_t fzero_count_launch(const FzeroArgs& a, cudaStream_t s);
+cudaError_t fzero_write_launch(const FzeroArgs& a, cudaStream_t s);
+size_t fzero_plane_words(uint64_t n);
 
 // One tuning point of the digit-pass kernel.
 struct Variant {

@@ -172,14 +172,16 @@ DigitOp<K, F> make_op(const DigitConsts& dc, int bit, int nbits) {
   return op;
 }
 
-// Functor of the multi-pass sort's digit passes: floating keys travel between passes as their bit-ordered image.
-template <bool F>
-using PassOp = std::conditional_t<F, OrderedFloatOp<K>, DigitOp<K, false>>;
-template <bool F>
-PassOp<F> make_pass_op(const PassArgs& a) {
-  if constexpr (F) {
+// Functor of the multi-pass sort's digit passes.  FM 0: integer keys (DigitOp); 1: floating keys travelling between passes as
+// their bit-ordered image, zeros collapsed in every digit extraction (OrderedFloatOp); 2: first / last pass of a full-range sort
+// of 4- / 8-byte floating keys with zero recording (ImageFloatOp) -- the passes in between run as FM 0.
+template <int FM>
+using PassOp = std::conditional_t<FM == 2, ImageFloatOp<K>, std::conditional_t<FM == 1, OrderedFloatOp<K>, DigitOp<K, false>>>;
+template <int FM>
+PassOp<FM> make_pass_op(const PassArgs& a) {
+  if constexpr (FM != 0) {
     using W = typename WideOf<K>::type;
-    OrderedFloatOp<K> op;
+    PassOp<FM> op;
     op.xor_mask = (W)a.dc.xor_mask;
     op.bit = (uint32_t)a.bit;
     op.mask = a.nbits >= 32 ? 0xffffffffu : (1u << a.nbits) - 1u;
@@ -238,11 +240,13 @@ void fill_params(OnesweepParams<K, OpT>& p, const PassArgs& a, const OpT& op) {
   p.op = op;
   for (int i = 0; i < MAX_PEERS; ++i) p.peer_keys[i] = p.peer_vals[i] = nullptr;
   p.peer_capacity = ~0ull;
+  p.zero_z = a.zero_z;
+  p.zero_s = a.zero_s;
 }
 
-template <int V, bool F, typename OffT, int VI>
+template <int V, int F, typename OffT, int VI>
 cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
-  constexpr Variant c = variant_cfg<V, F, sizeof(OffT) == 8>(VI);
+  constexpr Variant c = variant_cfg<V, F == 1, sizeof(OffT) == 8>(VI);  // zero-recording float passes take the integer shapes
   constexpr int TILE = c.nt * c.ipt;
   OnesweepParams<K, PassOp<F>> p;
   fill_params(p, a, make_pass_op<F>(a));
@@ -252,7 +256,7 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
 #ifdef B2S_TUNING
   if constexpr (c.flow < 0) {
     using L = OnesweepSmem<K, V, c.nt, c.ipt>;
-    auto kern = onesweep_kernel<K, V, DigitOp<K, F>, OffT, c.nt, c.ipt, c.minb, LBW, false, c.abl, c.mode>;
+    auto kern = onesweep_kernel<K, V, DigitOp<K, F == 1>, OffT, c.nt, c.ipt, c.minb, LBW, false, c.abl, c.mode>;
     cudaError_t e = ensure_smem(kern, L::TOTAL);
     if (e != cudaSuccess) return e;
     unsigned long long grid = tiles;
@@ -281,14 +285,14 @@ cudaError_t launch_one(const PassArgs& a, cudaStream_t s) {
   }
 }
 
-template <int V, bool F, typename OffT, int... VI>
+template <int V, int F, typename OffT, int... VI>
 cudaError_t launch_vi(int variant, const PassArgs& a, cudaStream_t s, std::integer_sequence<int, VI...>) {
   cudaError_t r = cudaErrorInvalidValue;
   (void)((variant == VI ? (r = launch_one<V, F, OffT, VI>(a, s), true) : false) || ...);
   return r;
 }
 
-template <int V, bool F>
+template <int V, int F>
 cudaError_t launch_off(int variant, const PassArgs& a, cudaStream_t s) {
   using Seq = std::make_integer_sequence<int, NUM_VARIANTS>;
 #ifdef B2S_TUNING
@@ -303,11 +307,14 @@ cudaError_t launch_off(int variant, const PassArgs& a, cudaStream_t s) {
 template <int V>
 cudaError_t launch_f(int variant, const PassArgs& a, cudaStream_t s) {
 #ifndef B2S_TUNING
+  if constexpr (K >= 4 && (V == 0 || V == 4)) {
+    if (a.dc.is_float && a.zero_z != nullptr) return launch_off<V, 2>(variant, a, s);  // zero recording (b2s_fzero.cu)
+  }
   if constexpr (K >= 2) {
-    if (a.dc.is_float) return launch_off<V, true>(variant, a, s);
+    if (a.dc.is_float) return launch_off<V, 1>(variant, a, s);
   }
 #endif
-  return launch_off<V, false>(variant, a, s);
+  return launch_off<V, 0>(variant, a, s);
 }
 
 template <bool F, typename OffT>

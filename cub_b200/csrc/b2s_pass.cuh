@@ -64,6 +64,10 @@ struct OnesweepParams {
   void* peer_keys[MAX_PEERS];
   void* peer_vals[MAX_PEERS];
   unsigned long long peer_capacity;  // items per receive buffer: stores at or beyond it are dropped
+  // zero recording (ImageFloatOp, first pass of a full-range sort of floating keys; null otherwise): one word per row of 32
+  // input keys -- bit l of zero_z[r] = key 32 r + l is +-0.0, bit l of zero_s[r] = its sign bit (b2s_fzero.cu restores them)
+  unsigned int* zero_z;
+  unsigned int* zero_s;
 };
 
 // Shared-memory plan.  TMAW pads every digit run to the 16-byte phase of its destination: A = items per 16 bytes of the
@@ -349,6 +353,30 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   op.prepare();  // no-op for DigitOp; loads the device-resident splitters for SplitterOp
   if constexpr (CONV) {
     if (op.raw_in) {
+      if constexpr (OpRecordsZeros<OpT>::value) {
+        if (P.zero_z != nullptr) {
+          // rows of this warp are consecutive rows of the input: lane j keeps the words of row (u & ~31) + j, one coalesced store
+          // per 32 rows.  The sign ballot runs only for rows that hold a zero (warp-uniform branch).
+          const unsigned long long row0 = tile_now() * (unsigned long long)(TILE / 32) + (unsigned long long)(warp * IPT);
+          unsigned int zw = 0, sw = 0;
+#pragma unroll
+          for (int u = 0; u < IPT; ++u) {
+            const unsigned int bz = __ballot_sync(0xffffffffu, OpT::is_zero(key[u]));
+            unsigned int bs = 0;
+            if (bz) bs = __ballot_sync(0xffffffffu, (key[u] & OpT::HIGH) != 0);
+            if (lane == (u & 31)) {
+              zw = bz;
+              sw = bs;
+            }
+            if ((u & 31) == 31 || u == IPT - 1) {
+              if (lane <= (u & 31)) {
+                P.zero_z[row0 + (u & ~31) + lane] = zw;
+                P.zero_s[row0 + (u & ~31) + lane] = sw;
+              }
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < IPT; ++u) key[u] = op.to_image(key[u]);
     }

@@ -201,6 +201,12 @@ int b2s_set_tile_claim(int enable);
  * passes instead; b2s_set_counting_min_items(key_bytes = 1 | 2, n) sets the cut-over (defaults: 2^16 items for 1-byte keys, 2^22 for 2-byte integers, 2^23 for f16 / bf16 -- where the counting path overtakes the digit passes on a B200; setting key_bytes = 2 sets both 2-byte cut-overs).  Both
  * return the previous setting. */
 int b2s_set_counting_sort(int enable);
+/* Sorts of 4- / 8-byte floating keys over ALL their bits (no values or 4-byte values, more than one tile) give -0.0 and +0.0 one
+ * image in the first digit pass, record which keys were zeros and their signs (two bits per key of temporary storage), and
+ * restore the signs in the run of zeros after the last pass: digits then cost what integer digits cost in every pass, results
+ * are bit-identical.  b2s_set_float_zero_recording(0) / B2S_FLOAT_ZERO_RECORD=0 keeps the reference's scheme (zeros collapsed
+ * in every digit extraction).  Returns the previous setting. */
+int b2s_set_float_zero_recording(int enable);
 uint64_t b2s_set_counting_min_items(int key_bytes, uint64_t min_items);
 /* Tuning builds: digit pass number `pass` of every following sort writes per-tile phase timestamps (u64[tiles][16], SM clock
  * cycles; slot 0 = global timer in ns, slot 15 = SM id) to d_trace when the active variant is a trace variant.  NULL disables. */
