@@ -143,11 +143,11 @@ struct ImageFloatOp {
 
   __device__ __forceinline__ void prepare() {}
   __host__ __device__ __forceinline__ static bool is_zero(W k) { return (k & (ONES ^ HIGH)) == 0; }  // +0.0 or -0.0 (raw)
-  __host__ __device__ __forceinline__ W to_image(W k) const {
+  __host__ __device__ __forceinline__ W to_image_nz(W k) const {  // image of a key that is not a zero
     const W m = KBYTES == 8 ? (W)((long long)k >> 63) : (W)((int)((unsigned int)k << (WBITS - KBITS)) >> 31);
-    const W t = (k ^ (m | HIGH) ^ xor_mask) & ONES;
-    return is_zero(k) ? HIGH : t;
+    return (k ^ (m | HIGH) ^ xor_mask) & ONES;
   }
+  __host__ __device__ __forceinline__ W to_image(W k) const { return is_zero(k) ? HIGH : to_image_nz(k); }
   __host__ __device__ __forceinline__ W to_raw(W t) const {
     const W o = t ^ xor_mask;
     const W m = KBYTES == 8 ? (W)((long long)o >> 63) : (W)((int)((unsigned int)o << (WBITS - KBITS)) >> 31);

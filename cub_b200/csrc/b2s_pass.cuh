@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
   op.prepare();  // no-op for DigitOp; loads the device-resident splitters for SplitterOp
   if constexpr (CONV) {
     if (op.raw_in) {
+      bool converted = false;
       if constexpr (OpRecordsZeros<OpT>::value) {
         if (P.zero_z != nullptr) {
           // rows of this warp are consecutive rows of the input: lane j keeps the words of row (u & ~31) + j, one coalesced store
@@ -361,9 +362,11 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
           unsigned int zw = 0, sw = 0;
 #pragma unroll
           for (int u = 0; u < IPT; ++u) {
-            const unsigned int bz = __ballot_sync(0xffffffffu, OpT::is_zero(key[u]));
+            const W k = key[u];
+            const bool z = OpT::is_zero(k);
+            const unsigned int bz = __ballot_sync(0xffffffffu, z);
             unsigned int bs = 0;
-            if (bz) bs = __ballot_sync(0xffffffffu, (key[u] & OpT::HIGH) != 0);
+            if (bz) bs = __ballot_sync(0xffffffffu, (k & OpT::HIGH) != 0);
             if (lane == (u & 31)) {
               zw = bz;
               sw = bs;
@@ -374,11 +377,15 @@ __global__ void __launch_bounds__(NT, MINB) digit_pass_kernel(const OnesweepPara
                 P.zero_s[row0 + (u & ~31) + lane] = sw;
               }
             }
+            key[u] = z ? OpT::HIGH : op.to_image_nz(k);
           }
+          converted = true;
         }
       }
+      if (!converted) {
 #pragma unroll
-      for (int u = 0; u < IPT; ++u) key[u] = op.to_image(key[u]);
+        for (int u = 0; u < IPT; ++u) key[u] = op.to_image(key[u]);
+      }
     }
   }
   unsigned int* myhist = whist + warp * RADIX;
