@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${1:-r2q}.json 2> gpurun_out/bench_${1:-r2q}.err; echo "bench exit $?"
-python - <<'PY'
+python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_${1:-r2q}.json"))
 print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["avg_launch_ms"], d["e2e"]["value"])
