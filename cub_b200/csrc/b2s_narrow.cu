@@ -6,17 +6,18 @@
 // bit pattern, so that the stable order of equal keys cannot be observed in the result: the output is a function of the joint
 // histogram of the keys alone and is produced here by
 //   1. joint_hist16_kernel / the ordinary histogram kernel (8-bit keys): one read of the keys -> counts of all 2^bits images,
-//   2. prefix_kernel: exclusive prefix over the images in sort order,
+//   2. prefix16_kernel: exclusive prefix over the images in sort order,
 //   3. expand_kernel: every 16-byte piece of the output looks up its image (binary search in the prefix array, L1/L2
 //      resident) and is written with one 128-bit store,
 // i.e. 2*K bytes of traffic per key.  The ONE exception to "same digits => same bits" are the floating zeros: -0.0 and +0.0
 // share their digits (cub/block/radix_rank_sort_operations.cuh:55-66, 79-89) but not their bits, so the reference leaves them
 // interleaved in input order inside one run.  Their images are neighbours (ZERO_IMG, HIGH), the expansion writes the run, and
-// when BOTH occur (device-side flag) three small kernels re-create the input order: per-tile counts of zero-like keys, an
-// exclusive scan over the tiles, and a stable compaction of the zero-like input keys into the run (one more read of the
-// keys each; skipped on the device when one of the two zeros is absent).  Results are bit-identical to the digit passes.
+// when BOTH occur (device-side flag written by the prefix kernel) two more kernels re-create the input order: zero_count16
+// reads the keys once more and leaves one "is a zero" bit per key plus one count per CTA range, zero_write16 walks the bit
+// masks and copies the zeros input -> run in order (both exit at once when one of the two zeros is absent).  Results are
+// bit-identical to the digit passes.
 //
-// Roofline: HBM, algorithmic bytes per key = 2*K (+ 2*K for the two zero kernels when both zeros occur).
+// Roofline: HBM, algorithmic bytes per key = 2*K (+ K + 1/4 for the two zero kernels when both zeros occur).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
