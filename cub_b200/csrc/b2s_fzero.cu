@@ -6,7 +6,7 @@
 // key is a zero, S: its sign bit -- after which the zeros are ordinary equal keys: the passes are stable, so they arrive at the
 // output as one run in input order, at the offset of digit 0x80 of the top pass (the zeros' image is the smallest one with that
 // top digit).  The two kernels below give the run its signs back: per-CTA counts of the Z plane, then every CTA walks its
-// contiguous range of the planes (1/32 + 1/32 of a bit... n/8 bytes each) and stores +0.0 or -0.0 at run start + rank.
+// contiguous range of the planes (one bit per key each: n/8 bytes) and stores +0.0 or -0.0 at run start + rank.
 // Cost: two ballots per 32 keys in the first pass and ~n/4 bytes of extra traffic; gain: digits cost 2 instructions instead
 // of 4 in every pass, the passes in between ARE the integer kernels with their shapes.
 #include <cuda_runtime.h>
