@@ -95,6 +95,45 @@ def test_temp_storage_query_on_cpu(b2s):
     assert b2s.b2s_radix_sort(None, None, None, None, None, None, 10, 6, 0, 4, 0, 0, 8, None) != 0
 
 
+def test_size_queries_of_the_counting_path_and_of_zero_recording(b2s):
+    """Temp-storage sizes follow the path a sort will take (decided from its arguments alone, so that the query and the sort
+    agree): the counting path needs no alternate buffer; zero recording adds two bits per key; the switches restore the plain
+    digit-pass sizes.  No GPU work."""
+    n = 1 << 26
+    # u16 keys alone, all bits: 2 x 512 KB of counters / prefix instead of an n * 2-byte alternate buffer
+    cnt = _query(b2s, n, 2, 0)
+    assert cnt < (2 << 20)
+    # bf16: + one bit per key for the zeros
+    assert n // 8 <= _query(b2s, n, 5, 0) - cnt < n // 8 + (1 << 20)
+    old = b2s.b2s_set_counting_sort(0)
+    try:
+        assert _query(b2s, n, 2, 0) >= n * 2
+    finally:
+        assert b2s.b2s_set_counting_sort(old) == 0
+    # below the cut-over, with values or with a partial bit range: digit passes
+    assert _query(b2s, 1 << 20, 2, 0) >= (1 << 20) * 2
+    assert _query(b2s, n, 2, 4) >= n * 6
+    assert _query(b2s, n, 2, 0, 0, 15) >= n * 2
+    prev = b2s.b2s_set_counting_min_items(2, 1 << 30)
+    try:
+        assert prev == 1 << 22 and _query(b2s, n, 2, 0) >= n * 2
+    finally:
+        b2s.b2s_set_counting_min_items(2, prev)
+        b2s.b2s_set_counting_min_items(1, b2s.b2s_set_counting_min_items(1, 1 << 16))
+    # f32 keys, DoubleBuffer form: bookkeeping + two bits per key; without recording: bookkeeping only
+    rec = _query(b2s, n, 8, 0, db=True)
+    old = b2s.b2s_set_float_zero_recording(0)
+    try:
+        plain = _query(b2s, n, 8, 0, db=True)
+    finally:
+        assert b2s.b2s_set_float_zero_recording(old) == 0
+    # (the recording sort runs on the integer tile shapes: fewer tiles, smaller status arrays than `plain`)
+    assert rec >= n // 4 and plain < n // 4 and rec - plain < n // 4 + (4 << 20)
+    # partial bit ranges and 8-byte values do not record
+    assert _query(b2s, n, 8, 0, 1, 31, db=True) < (64 << 20)
+    assert _query(b2s, n, 8, 8, db=True) < (64 << 20)
+
+
 def test_variant_description(b2s):
     nt, ipt, minb, match = (ctypes.c_int() for _ in range(4))
     nv = b2s.b2s_describe_variant(4, 4, 0, ctypes.byref(nt), ctypes.byref(ipt), ctypes.byref(minb), ctypes.byref(match))
